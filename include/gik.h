@@ -1,0 +1,152 @@
+/* gik.h -- C ABI of the B200-native batched dual-arm grasp-pose IK library (libgik.so).
+ *
+ * The reference (Ulixes-8/Motion-Planning-and-Control-for-Dual-Manipulator-Robot) is pure Python and
+ * has no FFI layer of its own; its boundary for this path is the Python function
+ *     computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None) -> (q, success)
+ * (inverse_geometry.py:17,100).  The entry points below are what a reference-side binding (ctypes, see
+ * INTEGRATION.md) calls to replace the body of that function and of its two batch callers
+ * (path.py:57 sampling, path.py:125-163 edge projection).  Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *   - Plain C, no CUDA or torch types.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - All data pointers are DEVICE pointers owned by the caller.  The handle owns only the constant
+ *     kinematic table.  Launches are asynchronous on `stream`; the caller synchronises.
+ *   - Return value: 0 = ok, negative = invalid argument / unsupported model (GIK_E_*),
+ *     positive = a cudaError_t value.  No exceptions cross the ABI.
+ *   - A handle is immutable after gik_create: concurrent calls on different streams are safe.
+ *   - Batch layout is structure-of-arrays, component-major: element (c, i) of a [C][n] array lives at
+ *     ptr[c * n + i], so consecutive problems are consecutive addresses.
+ *       q      : [nq][n]           joint configuration, pinocchio order (q index = joint id - 1)
+ *       pose   : [12][n]           cube placement: rows 0-8 rotation row-major, rows 9-11 translation
+ *       frames : [2][12][n]        LARM_EFF, RARM_EFF world placements, same 12-row layout
+ *       jac    : [2][6][nq][n]     LOCAL frame Jacobians, rows [linear(3); angular(3)]
+ *       resid  : [2][n]            ||log6(hand^-1 * hook)|| for left, right
+ */
+#ifndef GIK_H_
+#define GIK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIK_MAX_NQ 32
+
+/* error codes (negative); positive return values are cudaError_t */
+#define GIK_OK                 0
+#define GIK_E_NULL            -1   /* null pointer argument */
+#define GIK_E_SIZE            -2   /* negative / oversized count */
+#define GIK_E_MODEL           -3   /* kinematic table is not a tree of 1-dof revolute joints */
+#define GIK_E_TOPOLOGY        -4   /* table does not match the compiled torso + two 6R-arm fast path */
+#define GIK_E_PARAM           -5   /* bad solver parameter (eps<=0, dt<=0, max_iters<0, damping<0) */
+#define GIK_E_HANDLE          -6   /* bad or destroyed handle */
+
+/* Host-side flattened kinematic model: what the reference obtains from
+ * RobotWrapper.BuildFromURDF + translaterobot (setup_pinocchio.py:28-32,73-75) and from the cube's
+ * hook frames (setup_pinocchio.py:44-50, tools.py:54-59).  All joints are 1-dof revolute about a
+ * coordinate axis (pinocchio JointModelRX/RY/RZ), listed in q order with parents first. */
+typedef struct gik_table_s {
+  int32_t nq;                        /* number of joints = size of q (15 for Nextage) */
+  int32_t parent[GIK_MAX_NQ];        /* parent q index, -1 = universe */
+  int32_t axis[GIK_MAX_NQ];          /* 0 = x, 1 = y, 2 = z */
+  double  joint_R[GIK_MAX_NQ][9];    /* model.jointPlacements[i+1].rotation, row-major */
+  double  joint_p[GIK_MAX_NQ][3];    /* model.jointPlacements[i+1].translation */
+  double  lower[GIK_MAX_NQ];         /* model.lowerPositionLimit */
+  double  upper[GIK_MAX_NQ];         /* model.upperPositionLimit */
+  int32_t hand_joint[2];             /* q index of the joint carrying LARM_EFF / RARM_EFF (config.py:25-26) */
+  double  hand_R[2][9];              /* model.frames[getFrameId(hand)].placement.rotation */
+  double  hand_p[2][3];
+  double  hook_R[2][9];              /* cube.data.oMf[getFrameId(LARM_HOOK / RARM_HOOK)] (config.py:28-29) */
+  double  hook_p[2][3];
+} gik_table_t;
+
+/* Solver parameters.  Defaults reproduce the reference literals:
+ * eps = EPSILON = 1e-3 (config.py:22), dt = DT = 1e-2 and max_iters = 1000 (inverse_geometry.py:53-54),
+ * damping = 0 (undamped pseudo-inverse, inverse_geometry.py:83). */
+typedef struct gik_params_s {
+  double  eps;        /* per-hand convergence tolerance on ||log6||_2 */
+  double  dt;         /* step length: q <- clamp(q + dt * J^+ e) */
+  double  damping;    /* lambda in J^T (J J^T + lambda I)^-1 e; 0 = pseudo-inverse */
+  int32_t max_iters;  /* iteration cap */
+  int32_t flags;      /* reserved, must be 0 */
+} gik_params_t;
+
+typedef struct gik_handle_s* gik_handle_t;
+
+/* Fills `p` with the reference defaults above. */
+void gik_default_params(gik_params_t* p);
+
+/* Validates `host_table`, derives the fast-path constants and uploads them to `device`. */
+int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out);
+int gik_destroy(gik_handle_t h);
+
+/* K1. Replaces pin.framesForwardKinematics + data.oMf[LARM_EFF / RARM_EFF]
+ * (inverse_geometry.py:58,62-63).  q [nq][n] -> frames [2][12][n]. */
+int gik_fk_f32(gik_handle_t h, int64_t n, const float* q, float* frames, void* stream);
+int gik_fk_f64(gik_handle_t h, int64_t n, const double* q, double* frames, void* stream);
+
+/* K2. Replaces pin.computeFrameJacobian(model, data, q, frame_id) for both hands, LOCAL reference
+ * frame (inverse_geometry.py:75-76).  q [nq][n] -> jac [2][6][nq][n]. */
+int gik_jac_f32(gik_handle_t h, int64_t n, const float* q, float* jac, void* stream);
+int gik_jac_f64(gik_handle_t h, int64_t n, const double* q, double* jac, void* stream);
+
+/* K3. Replaces the descent loop of computeqgrasppose (inverse_geometry.py:49-94) for n independent
+ * problems, without the collision() term of the predicate at :70 (applied by the caller, see
+ * INTEGRATION.md).  q_init [nq][n], pose [12][n] -> q_out [nq][n], converged [n] (1 = the loop broke
+ * with both residuals < eps), iters [n] (updates applied), resid [2][n] (residuals at q_out).
+ * `iters` and `resid` may be NULL. */
+int gik_solve_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose,
+                  const gik_params_t* params, float* q_out, uint8_t* converged, int32_t* iters,
+                  float* resid, void* stream);
+int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose,
+                  const gik_params_t* params, double* q_out, uint8_t* converged, int32_t* iters,
+                  double* resid, void* stream);
+
+/* K4. Best-of-restarts reduction (new; BASELINE config 3).  Problem (p, r) of a [n_place x n_restart]
+ * solve is stored at index p * n_restart + r.  Picks, per placement, the converged candidate with the
+ * smallest max(resid_L, resid_R); ties -> lowest restart index; if none converged, the smallest
+ * residual overall with converged = 0.  q [nq][n_place*n_restart] -> q_best [nq][n_place],
+ * conv_best [n_place], which [n_place] (restart index chosen; may be NULL). */
+int gik_best_of_f32(gik_handle_t h, int64_t n_place, int32_t n_restart, const float* q,
+                    const uint8_t* converged, const float* resid, float* q_best, uint8_t* conv_best,
+                    int32_t* which, void* stream);
+int gik_best_of_f64(gik_handle_t h, int64_t n_place, int32_t n_restart, const double* q,
+                    const uint8_t* converged, const double* resid, double* q_best, uint8_t* conv_best,
+                    int32_t* which, void* stream);
+
+/* K5. Replaces the loop of project_path (path.py:137-160) for n_edges independent edges: for
+ * step = 1..num_steps[e] the cube placement is SE3.Interpolate(pose_a, pose_b, step / num_steps[e])
+ * (path.py:139-141) and the IK is warm-started from the previous step's q (path.py:152);
+ * the march stops at the first non-converged step (path.py:153-156).
+ * q_start [nq][E], pose_a / pose_b [12][E], num_steps [E] (1..max_steps) ->
+ * q_path [max_steps][nq][E] (rows >= n_valid[e] are left untouched), n_valid [E] (converged steps),
+ * iters_total [E] (descent iterations executed on the edge; may be NULL). */
+int gik_project_edges_f32(gik_handle_t h, int64_t n_edges, int32_t max_steps, const float* q_start,
+                          const float* pose_a, const float* pose_b, const int32_t* num_steps,
+                          const gik_params_t* params, float* q_path, int32_t* n_valid,
+                          int32_t* iters_total, void* stream);
+int gik_project_edges_f64(gik_handle_t h, int64_t n_edges, int32_t max_steps, const double* q_start,
+                          const double* pose_a, const double* pose_b, const int32_t* num_steps,
+                          const gik_params_t* params, double* q_path, int32_t* n_valid,
+                          int32_t* iters_total, void* stream);
+
+/* Measurement helpers (bench.py). */
+/* Algorithmic FLOPs of ONE descent iteration of ONE dual-arm problem (SURVEY.md 8d breakdown). */
+size_t gik_flops_per_iter(void);
+/* Algorithmic bytes moved per solve (inputs + outputs), elem_size = 4 or 8. */
+size_t gik_bytes_per_solve(int elem_size);
+/* Runs a register-resident FMA chain on every SM and returns the achieved TFLOP/s (FMA = 2 FLOP) of the
+ * FP32 (elem_size 4) or FP64 (elem_size 8) CUDA-core pipe in *tflops; synchronous. */
+int gik_measure_fma_peak(int device, int elem_size, int repeats, double* tflops);
+/* Grid the solver launches for n problems on the handle's device (for gpu_launches / occupancy reports). */
+int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blocks, int32_t* threads);
+
+const char* gik_strerror(int code);
+const char* gik_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIK_H_ */

@@ -1,0 +1,357 @@
+// gik_core.cuh -- per-problem arithmetic of the dual-arm grasp IK, one problem per thread, everything in
+// registers.  Compiles for the device (nvcc, sm_100a) and -- for the CPU unit tests under tests/hostsim
+// only -- as plain C++17.  Nothing here touches memory except through the DevTable reference, which on the
+// device is a __constant__ object (constant-bank operands feed the FMAs directly).
+//
+// What one iteration computes (reference: inverse_geometry.py:56-89):
+//   FK of both hands + both LOCAL frame Jacobians    (pin.framesForwardKinematics :58, computeFrameJacobian :75-76)
+//   e_h = log6(hand_h^-1 * hook_h)                   (pin.log :66-67)
+//   dq  = J^T (J J^T + lambda I)^-1 [e_L; e_R]       (np.linalg.pinv(J) @ error :83, lambda = 0)
+// and the caller applies q <- clamp(q + dt dq)       (pin.integrate :86, projecttojointlimits :89).
+//
+// Structure that is exploited (DESIGN.md "Kernel math"):
+//   * Each hand's chain is walked BACKWARDS from the hand frame, carrying the pose of the current joint
+//     expressed in the hand frame.  That yields the LOCAL Jacobian columns directly (no world-frame FK, no
+//     R_f^T rotations) and ends at hand^-1, which is exactly what the error needs.
+//   * J = [c_L A_L 0; c_R 0 A_R] (chest column + two 6x6 arm blocks), so
+//     J J^T + lambda I = blockdiag(A_L A_L^T + lambda I, A_R A_R^T + lambda I) + c c^T :
+//     two 6x6 Cholesky factorisations and a Sherman-Morrison rank-1 correction replace the dense 12x12 solve.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GIK_HD __host__ __device__ __forceinline__
+#else
+#define GIK_HD inline __attribute__((always_inline))
+#endif
+
+#ifndef GIK_MAX_NQ
+#define GIK_MAX_NQ 32
+#endif
+
+namespace gik {
+
+constexpr int kActive = 13;  // chest + 6 + 6 joints that move the hands
+
+// Axis of chain joint k (k = 0: chest, k = 1..6: arm joints root -> tip).  This pattern (z | z y y x y z) is
+// the compiled-in structure of the fast path; gik_create() rejects tables that do not match it.
+GIK_HD constexpr int chain_axis(int k) {
+  return k == 0 ? 2 : k == 1 ? 2 : k == 2 ? 1 : k == 3 ? 1 : k == 4 ? 0 : k == 5 ? 1 : 2;
+}
+
+template <typename T>
+struct ArmConst {
+  T t[7][3];    // parent -> joint translation of chain joint k
+  T finv_R[9];  // (hand frame offset on the tip joint)^-1, row-major
+  T finv_p[3];
+  T hook_R[9];  // hook frame on the cube
+  T hook_p[3];
+};
+
+template <typename T>
+struct DevTable {
+  ArmConst<T> arm[2];
+  T lo[kActive], hi[kActive];          // limits of the active joints: 0 chest, 1-6 left, 7-12 right
+  T qlo[GIK_MAX_NQ], qhi[GIK_MAX_NQ];  // limits in q order (passive joints)
+  int32_t nq;
+  int32_t act_q[kActive];              // q index of each active joint
+  int32_t n_passive;
+  int32_t passive_q[GIK_MAX_NQ];
+};
+
+// ------------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------------
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr float kPivotFloor = 1e-30f;  // Cholesky pivot guard (singular arm Jacobian)
+  static constexpr float kSeriesT2 = 0.25f;     // theta^2 below which log6's alpha/beta use their series
+  static constexpr float kTinyS = 1e-18f;
+};
+template <> struct Num<double> {
+  static constexpr double kPivotFloor = 1e-280;
+  static constexpr double kSeriesT2 = 1e-4;
+  static constexpr double kTinyS = 1e-150;
+};
+
+GIK_HD float rsqrt_(float x) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+GIK_HD double rsqrt_(double x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+GIK_HD float div_(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+GIK_HD double div_(double a, double b) { return a / b; }
+GIK_HD float sqrt_(float x) { return sqrtf(x); }
+GIK_HD double sqrt_(double x) { return sqrt(x); }
+GIK_HD float atan2_(float y, float x) { return atan2f(y, x); }
+GIK_HD double atan2_(double y, double x) { return atan2(y, x); }
+GIK_HD float max_(float a, float b) { return fmaxf(a, b); }
+GIK_HD double max_(double a, double b) { return fmax(a, b); }
+GIK_HD float min_(float a, float b) { return fminf(a, b); }
+GIK_HD double min_(double a, double b) { return fmin(a, b); }
+
+// FAST = MUFU-based sin/cos (abs error ~5e-7 on [-pi, pi]); accurate otherwise.
+template <bool FAST>
+GIK_HD void sincos_(float x, float& s, float& c) {
+#ifdef __CUDA_ARCH__
+  if (FAST) __sincosf(x, &s, &c); else sincosf(x, &s, &c);
+#else
+  s = sinf(x); c = cosf(x);
+#endif
+}
+template <bool FAST>
+GIK_HD void sincos_(double x, double& s, double& c) {
+#ifdef __CUDA_ARCH__
+  sincos(x, &s, &c);
+#else
+  s = sin(x); c = cos(x);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// log6: SE3 (R row-major, p) -> [v; w].  Same function as pinocchio's log6/log3 (pin.log at
+// inverse_geometry.py:66-67); theta is taken as atan2(|vee(R - R^T)|/2, (tr R - 1)/2), which equals
+// acos((tr R - 1)/2) for a rotation matrix but stays accurate in fp32 near theta = 0.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
+  const T vx = R[7] - R[5], vy = R[2] - R[6], vz = R[3] - R[1];
+  const T tr = R[0] + R[4] + R[8];
+  const T c = min_(max_((tr - T(1)) * T(0.5), T(-1)), T(1));
+  const T s = T(0.5) * sqrt_(vx * vx + vy * vy + vz * vz);
+  const T theta = atan2_(s, c);
+  T wx, wy, wz;
+  if (theta >= T(3.14159265358979323846 - 1e-2)) {
+    // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
+    const T cphi = -c;
+    const T beta = theta * theta / (T(1) + cphi);
+    const T t0 = (R[0] + cphi) * beta, t1 = (R[4] + cphi) * beta, t2 = (R[8] + cphi) * beta;
+    wx = (vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
+    wy = (vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
+    wz = (vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
+  } else {
+    const T fac = s > Num<T>::kTinyS ? T(0.5) * div_(theta, s) : T(0.5);  // theta / (2 sin theta)
+    wx = fac * vx; wy = fac * vy; wz = fac * vz;
+  }
+  const T t2 = theta * theta;
+  // alpha = (theta/2) cot(theta/2), beta = (1 - alpha) / theta^2; cot(theta/2) = (1+c)/s = s/(1-c)
+  const bool front = c >= T(0);
+  const T num = front ? T(1) + c : s;
+  const T den = front ? s : T(1) - c;
+  T alpha = T(0.5) * theta * div_(num, max_(den, Num<T>::kTinyS));
+  T beta = div_(T(1) - alpha, max_(t2, Num<T>::kTinyS));
+  if (t2 < Num<T>::kSeriesT2) {
+    alpha = T(1) - t2 * (T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * T(1.0 / 30240)));
+    beta = T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * (T(1.0 / 30240) + t2 * T(1.0 / 1209600)));
+  }
+  const T wp = beta * (wx * p[0] + wy * p[1] + wz * p[2]);
+  e[0] = alpha * p[0] - T(0.5) * (wy * p[2] - wz * p[1]) + wp * wx;
+  e[1] = alpha * p[1] - T(0.5) * (wz * p[0] - wx * p[2]) + wp * wy;
+  e[2] = alpha * p[2] - T(0.5) * (wx * p[1] - wy * p[0]) + wp * wz;
+  e[3] = wx; e[4] = wy; e[5] = wz;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Backward walk of one hand's chain.  (B, b) is the pose of the current joint frame expressed in the hand
+// frame; A[:, K] receives the LOCAL Jacobian column of chain joint K ([linear; angular]).  On return (B, b)
+// is hand^-1 in the world.  OFF maps chain joint K >= 1 to its slot in the active-joint arrays.
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int K, int OFF>
+GIK_HD void chain_step(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
+                       T (&b)[3], T (&A)[6][7]) {
+  constexpr int AX = chain_axis(K), I = (AX + 1) % 3, J = (AX + 2) % 3;
+  constexpr int SLOT = K == 0 ? 0 : OFF + K;
+  const T ax = B[AX], ay = B[3 + AX], az = B[6 + AX];
+  A[0][K] = b[1] * az - b[2] * ay;
+  A[1][K] = b[2] * ax - b[0] * az;
+  A[2][K] = b[0] * ay - b[1] * ax;
+  A[3][K] = ax; A[4][K] = ay; A[5][K] = az;
+  const T c = cs[SLOT], s = sn[SLOT];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // B <- B * Rot(axis, -q)
+    const T bi = B[3 * r + I], bj = B[3 * r + J];
+    B[3 * r + I] = c * bi - s * bj;
+    B[3 * r + J] = s * bi + c * bj;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)    // b <- b - B * t
+    b[r] -= B[3 * r] * ac.t[K][0] + B[3 * r + 1] * ac.t[K][1] + B[3 * r + 2] * ac.t[K][2];
+  if constexpr (K > 0) chain_step<T, K - 1, OFF>(ac, cs, sn, B, b, A);
+}
+
+template <typename T, int OFF>
+GIK_HD void hand_chain(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
+                       T (&b)[3], T (&A)[6][7]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) b[i] = ac.finv_p[i];
+  chain_step<T, 6, OFF>(ac, cs, sn, B, b, A);
+}
+
+// hook target of one hand: cube * hook offset (tools.getcubeplacement, tools.py:54-59)
+template <typename T>
+GIK_HD void hook_target(const ArmConst<T>& ac, const T (&cube)[12], T (&tgt)[12]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      tgt[3 * r + c] = cube[3 * r] * ac.hook_R[c] + cube[3 * r + 1] * ac.hook_R[3 + c] +
+                       cube[3 * r + 2] * ac.hook_R[6 + c];
+    tgt[9 + r] = cube[9 + r] + cube[3 * r] * ac.hook_p[0] + cube[3 * r + 1] * ac.hook_p[1] +
+                 cube[3 * r + 2] * ac.hook_p[2];
+  }
+}
+
+// e = log6(hand^-1 * target), hand^-1 = (B, b)
+template <typename T>
+GIK_HD void hand_error(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], T (&e)[6]) {
+  T R[9], p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      R[3 * r + c] = B[3 * r] * tgt[c] + B[3 * r + 1] * tgt[3 + c] + B[3 * r + 2] * tgt[6 + c];
+    p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
+  }
+  log6(R, p, e);
+}
+
+// One hand's share of the damped least-squares step.  Returns u = A^T G^-1 e, w = A^T G^-1 c over the six
+// arm joints (G = A A^T + lambda I, A = arm block, c = chest column) and accumulates c.G^-1 e, c.G^-1 c.
+template <typename T, int OFF>
+GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive],
+                      const T (&tgt)[12], T lambda, T (&u)[6], T (&w)[6], T& Sy, T& Sz, T& resid) {
+  T B[9], b[3], A[6][7], e[6];
+  hand_chain<T, OFF>(ac, cs, sn, B, b, A);
+  hand_error(B, b, tgt, e);
+  resid = sqrt_(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+
+  // Cholesky of G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle, in place; inv[j] = 1 / L[j][j]
+  T L[6][6], inv[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      T g = A[i][1] * A[j][1];
+#pragma unroll
+      for (int k = 2; k <= 6; ++k) g += A[i][k] * A[j][k];
+      L[i][j] = (i == j) ? g + lambda : g;
+    }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    T d = L[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    inv[j] = rsqrt_(max_(d, Num<T>::kPivotFloor));
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      T v = L[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv[j];
+    }
+  }
+  // two right-hand sides: y = G^-1 e, z = G^-1 c  (c = A[:,0])
+  T y[6], z[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    T a = e[j], cc = A[j][0];
+#pragma unroll
+    for (int k = 0; k < j; ++k) { a -= L[j][k] * y[k]; cc -= L[j][k] * z[k]; }
+    y[j] = a * inv[j]; z[j] = cc * inv[j];
+  }
+#pragma unroll
+  for (int j = 5; j >= 0; --j) {
+    T a = y[j], cc = z[j];
+#pragma unroll
+    for (int k = j + 1; k < 6; ++k) { a -= L[k][j] * y[k]; cc -= L[k][j] * z[k]; }
+    y[j] = a * inv[j]; z[j] = cc * inv[j];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    T a = A[0][k + 1] * y[0], cc = A[0][k + 1] * z[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) { a += A[i][k + 1] * y[i]; cc += A[i][k + 1] * z[i]; }
+    u[k] = a; w[k] = cc;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { Sy += A[i][0] * y[i]; Sz += A[i][0] * z[i]; }
+}
+
+// One full iteration at q: residual norms of both hands and the step direction dq = J^+ e.
+template <typename T, bool FAST>
+GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T (&tgt)[2][12], T lambda,
+                         T (&dq)[kActive], T& residL, T& residR) {
+  T cs[kActive], sn[kActive];
+#pragma unroll
+  for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
+  T uL[6], wL[6], uR[6], wR[6], Sy = T(0), Sz = T(0);
+  hand_pass<T, 0>(tab.arm[0], cs, sn, tgt[0], lambda, uL, wL, Sy, Sz, residL);
+  hand_pass<T, 6>(tab.arm[1], cs, sn, tgt[1], lambda, uR, wR, Sy, Sz, residR);
+  const T kappa = div_(Sy, T(1) + Sz);
+  dq[0] = kappa;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    dq[1 + k] = uL[k] - kappa * wL[k];
+    dq[7 + k] = uR[k] - kappa * wR[k];
+  }
+}
+
+// q <- clamp(q + dt dq)  (pin.integrate on an all-revolute model :86, projecttojointlimits :89)
+template <typename T>
+GIK_HD void apply_step(const DevTable<T>& tab, T (&q)[kActive], const T (&dq)[kActive], T dt) {
+#pragma unroll
+  for (int i = 0; i < kActive; ++i) q[i] = min_(max_(tab.lo[i], q[i] + dt * dq[i]), tab.hi[i]);
+}
+
+// Residual norms only (no Jacobian use) -- used for the final evaluation of an exhausted problem.
+template <typename T, bool FAST>
+GIK_HD void fk_frames(const DevTable<T>& tab, const T (&q)[kActive], T (&frames)[2][12]) {
+  T cs[kActive], sn[kActive];
+#pragma unroll
+  for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
+  T B[9], b[3], A[6][7];
+  hand_chain<T, 0>(tab.arm[0], cs, sn, B, b, A);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // invert: R = B^T, p = -B^T b
+#pragma unroll
+    for (int c = 0; c < 3; ++c) frames[0][3 * r + c] = B[3 * c + r];
+    frames[0][9 + r] = -(B[r] * b[0] + B[3 + r] * b[1] + B[6 + r] * b[2]);
+  }
+  hand_chain<T, 6>(tab.arm[1], cs, sn, B, b, A);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) frames[1][3 * r + c] = B[3 * c + r];
+    frames[1][9 + r] = -(B[r] * b[0] + B[3 + r] * b[1] + B[6 + r] * b[2]);
+  }
+}
+
+template <typename T, bool FAST>
+GIK_HD void frame_jacobians(const DevTable<T>& tab, const T (&q)[kActive], T (&AL)[6][7], T (&AR)[6][7]) {
+  T cs[kActive], sn[kActive];
+#pragma unroll
+  for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
+  T B[9], b[3];
+  hand_chain<T, 0>(tab.arm[0], cs, sn, B, b, AL);
+  hand_chain<T, 6>(tab.arm[1], cs, sn, B, b, AR);
+}
+
+}  // namespace gik

@@ -1,0 +1,102 @@
+// gik_table.h -- host side: validate a gik_table_t (the flattened pinocchio model, include/gik.h) and derive
+// the constants of the compiled fast path (gik::DevTable<T>).  Plain C++17, no CUDA.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "../../include/gik.h"
+#include "gik_core.cuh"
+
+namespace gik {
+
+inline bool is_identity3(const double* R, double tol = 1e-12) {
+  for (int i = 0; i < 9; ++i)
+    if (fabs(R[i] - ((i % 4 == 0) ? 1.0 : 0.0)) > tol) return false;
+  return true;
+}
+
+// Limits are rounded INWARD when narrowed to T, so a clamped fp32 q never violates the fp64 limits
+// (tools.jointlimitsviolated, tools.py:17-19, tests q against the double-precision limits).
+template <typename T> inline T narrow_lo(double x) {
+  T v = (T)x;
+  if ((double)v < x) v = (T)nextafter(v, (T)INFINITY);
+  return v;
+}
+template <typename T> inline T narrow_hi(double x) {
+  T v = (T)x;
+  if ((double)v > x) v = (T)nextafter(v, (T)-INFINITY);
+  return v;
+}
+
+// Generic checks: a tree of 1-dof revolute joints with parents listed first.
+inline int validate_table(const gik_table_t& t) {
+  if (t.nq < 1 || t.nq > GIK_MAX_NQ) return GIK_E_MODEL;
+  for (int i = 0; i < t.nq; ++i) {
+    if (t.parent[i] < -1 || t.parent[i] >= i) return GIK_E_MODEL;
+    if (t.axis[i] < 0 || t.axis[i] > 2) return GIK_E_MODEL;
+    if (!(t.lower[i] <= t.upper[i])) return GIK_E_MODEL;
+  }
+  for (int h = 0; h < 2; ++h)
+    if (t.hand_joint[h] < 0 || t.hand_joint[h] >= t.nq) return GIK_E_MODEL;
+  return GIK_OK;
+}
+
+// Fast-path structure: both hands hang off 6-joint arms (axes z y y x y z, translation-only joint
+// placements) that share exactly one root joint (axis z, parent = universe).
+template <typename T>
+inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
+  int rc = validate_table(t);
+  if (rc != GIK_OK) return rc;
+  memset(&d, 0, sizeof(d));
+  int chain[2][7];
+  for (int h = 0; h < 2; ++h) {
+    int k = t.hand_joint[h];
+    for (int c = 6; c >= 0; --c) {
+      if (k < 0) return GIK_E_TOPOLOGY;
+      chain[h][c] = k;
+      k = t.parent[k];
+    }
+    if (k != -1) return GIK_E_TOPOLOGY;  // chain longer than 7
+    for (int c = 0; c < 7; ++c) {
+      const int j = chain[h][c];
+      if (t.axis[j] != chain_axis(c)) return GIK_E_TOPOLOGY;
+      if (!is_identity3(t.joint_R[j])) return GIK_E_TOPOLOGY;
+    }
+  }
+  if (chain[0][0] != chain[1][0]) return GIK_E_TOPOLOGY;
+  for (int a = 1; a < 7; ++a)
+    for (int b = 1; b < 7; ++b)
+      if (chain[0][a] == chain[1][b]) return GIK_E_TOPOLOGY;
+
+  d.nq = t.nq;
+  bool active[GIK_MAX_NQ] = {false};
+  for (int h = 0; h < 2; ++h) {
+    ArmConst<T>& ac = d.arm[h];
+    for (int c = 0; c < 7; ++c) {
+      const int j = chain[h][c];
+      for (int i = 0; i < 3; ++i) ac.t[c][i] = (T)t.joint_p[j][i];
+      const int slot = (c == 0) ? 0 : h * 6 + c;
+      d.act_q[slot] = j;
+      d.lo[slot] = narrow_lo<T>(t.lower[j]);
+      d.hi[slot] = narrow_hi<T>(t.upper[j]);
+      active[j] = true;
+    }
+    // inverse of the hand frame offset: (R, p)^-1 = (R^T, -R^T p)
+    const double* R = t.hand_R[h];
+    const double* p = t.hand_p[h];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) ac.finv_R[3 * r + c] = (T)R[3 * c + r];
+      ac.finv_p[r] = (T)(-(R[r] * p[0] + R[3 + r] * p[1] + R[6 + r] * p[2]));
+    }
+    for (int i = 0; i < 9; ++i) ac.hook_R[i] = (T)t.hook_R[h][i];
+    for (int i = 0; i < 3; ++i) ac.hook_p[i] = (T)t.hook_p[h][i];
+  }
+  for (int j = 0; j < t.nq; ++j) {
+    d.qlo[j] = narrow_lo<T>(t.lower[j]);
+    d.qhi[j] = narrow_hi<T>(t.upper[j]);
+    if (!active[j]) d.passive_q[d.n_passive++] = j;
+  }
+  return GIK_OK;
+}
+
+}  // namespace gik

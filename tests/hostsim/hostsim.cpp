@@ -1,0 +1,98 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE.  Compiles the device arithmetic of csrc/gik_core.cuh as plain C++ so the
+// `-m "not gpu"` tests can check the kernel math (fp32 and fp64) against the oracle without a GPU.  It is not
+// part of the product: the package never loads this library and there is no CPU fallback.
+// Same SoA layouts as include/gik.h, host pointers.
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../motion-planning-and-control-for-dual-manipulator-robot_b200/csrc/gik_table.h"
+
+using namespace gik;
+
+template <typename T>
+static int fk_impl(const gik_table_t* tab, int64_t n, const T* q, T* frames) {
+  DevTable<T> d;
+  int rc = build_dev_table<T>(*tab, d);
+  if (rc) return rc;
+  for (int64_t i = 0; i < n; ++i) {
+    T qa[kActive], fr[2][12];
+    for (int a = 0; a < kActive; ++a) qa[a] = q[(int64_t)d.act_q[a] * n + i];
+    fk_frames<T, true>(d, qa, fr);
+    for (int h = 0; h < 2; ++h)
+      for (int c = 0; c < 12; ++c) frames[((int64_t)h * 12 + c) * n + i] = fr[h][c];
+  }
+  return 0;
+}
+
+template <typename T>
+static int jac_impl(const gik_table_t* tab, int64_t n, const T* q, T* jac) {
+  DevTable<T> d;
+  int rc = build_dev_table<T>(*tab, d);
+  if (rc) return rc;
+  const int nq = d.nq;
+  for (int64_t i = 0; i < n; ++i) {
+    T qa[kActive], A[2][6][7];
+    for (int a = 0; a < kActive; ++a) qa[a] = q[(int64_t)d.act_q[a] * n + i];
+    frame_jacobians<T, true>(d, qa, A[0], A[1]);
+    for (int h = 0; h < 2; ++h)
+      for (int r = 0; r < 6; ++r) {
+        for (int j = 0; j < nq; ++j) jac[(((int64_t)h * 6 + r) * nq + j) * n + i] = T(0);
+        for (int k = 0; k < 7; ++k) {
+          const int slot = k == 0 ? 0 : h * 6 + k;
+          jac[(((int64_t)h * 6 + r) * nq + d.act_q[slot]) * n + i] = A[h][r][k];
+        }
+      }
+  }
+  return 0;
+}
+
+template <typename T>
+static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const T* pose,
+                      const gik_params_t* prm, T* q_out, uint8_t* conv, int32_t* iters, T* resid) {
+  DevTable<T> d;
+  int rc = build_dev_table<T>(*tab, d);
+  if (rc) return rc;
+  const T eps = (T)prm->eps, dt = (T)prm->dt, lambda = (T)prm->damping;
+  for (int64_t i = 0; i < n; ++i) {
+    T q[kActive], cube[12], tgt[2][12], dq[kActive], rL = 0, rR = 0;
+    for (int a = 0; a < kActive; ++a) q[a] = q_init[(int64_t)d.act_q[a] * n + i];
+    for (int c = 0; c < 12; ++c) cube[c] = pose[(int64_t)c * n + i];
+    hook_target(d.arm[0], cube, tgt[0]);
+    hook_target(d.arm[1], cube, tgt[1]);
+    int it = 0;
+    bool ok = false;
+    for (;;) {
+      ik_iteration<T, true>(d, q, tgt, lambda, dq, rL, rR);
+      ok = (rL < eps) && (rR < eps) && (it < prm->max_iters);
+      if (ok || it >= prm->max_iters) break;
+      apply_step(d, q, dq, dt);
+      ++it;
+    }
+    for (int a = 0; a < kActive; ++a) q_out[(int64_t)d.act_q[a] * n + i] = q[a];
+    for (int p = 0; p < d.n_passive; ++p) {
+      const int j = d.passive_q[p];
+      T v = q_init[(int64_t)j * n + i];
+      if (it > 0) v = min_(max_(d.qlo[j], v), d.qhi[j]);
+      q_out[(int64_t)j * n + i] = v;
+    }
+    conv[i] = ok ? 1 : 0;
+    if (iters) iters[i] = it;
+    if (resid) { resid[i] = rL; resid[n + i] = rR; }
+  }
+  return 0;
+}
+
+extern "C" {
+int hostsim_fk_f32(const gik_table_t* t, int64_t n, const float* q, float* f) { return fk_impl<float>(t, n, q, f); }
+int hostsim_fk_f64(const gik_table_t* t, int64_t n, const double* q, double* f) { return fk_impl<double>(t, n, q, f); }
+int hostsim_jac_f32(const gik_table_t* t, int64_t n, const float* q, float* j) { return jac_impl<float>(t, n, q, j); }
+int hostsim_jac_f64(const gik_table_t* t, int64_t n, const double* q, double* j) { return jac_impl<double>(t, n, q, j); }
+int hostsim_solve_f32(const gik_table_t* t, int64_t n, const float* q0, const float* pose, const gik_params_t* p,
+                      float* q, uint8_t* c, int32_t* it, float* r) {
+  return solve_impl<float>(t, n, q0, pose, p, q, c, it, r);
+}
+int hostsim_solve_f64(const gik_table_t* t, int64_t n, const double* q0, const double* pose, const gik_params_t* p,
+                      double* q, uint8_t* c, int32_t* it, double* r) {
+  return solve_impl<double>(t, n, q0, pose, p, q, c, it, r);
+}
+}
