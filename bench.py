@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- dual-arm grasp IK solves/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--dtype f32|f64]
+
+A "step" is ONE pass of the hot path over one batch of synthetic input: BASELINE config 2, 2^20 random cube
+placements over the table workspace (identity rotation, path.py:47), every problem started from q0 = 0,
+reference preset (eps 1e-3, dt 1e-2, max_iters 1000, undamped), fp32.  For N > 1 every rank solves its own
+2^20-problem slab (weak scaling, no data-path collective) and the step ends with the all-gather of (q, converged).
+
+Printed JSON (one line, rank 0): value = whole-job solves/s with inputs resident in HBM; e2e = the same metric
+through the public API with pinned HOST buffers (H2D + solve + D2H inside the timed region); roofline = the solve
+kernel against the CUDA-core FMA peak measured in the same run; cpu_baseline = the C oracle (a port of the
+reference's loop; the reference itself needs pinocchio, absent from this image) on the box's host cores.
+`--impl reference` times that CPU port alone."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1 << 20
+WORKSPACE_LO = (0.20, -0.40, 0.93)
+WORKSPACE_HI = (0.60, 0.40, 1.40)
+METRIC = "dual-arm grasp IK solves/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="problems per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, dtype):
+    return (f"config2: {n} random cube placements over the table workspace x[0.20,0.60] y[-0.40,0.40] z[0.93,1.40], "
+            f"identity rotation, single start q0=0, {dtype}, eps=1e-3 dt=1e-2 max_iters=1000 damping=0")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bounded sample of the same workload)
+# ----------------------------------------------------------------------------------------------------------
+def host_poses(n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    P = np.zeros((n, 12))
+    P[:, [0, 4, 8]] = 1.0
+    P[:, 9:] = rng.uniform(WORKSPACE_LO, WORKSPACE_HI, size=(n, 3))
+    return P
+
+
+def cpu_solve_rate(n_sample, seed=1234):
+    """Times the C oracle (oracle/grasp_ik_oracle.c, OpenMP over problems, all host threads) on n_sample problems
+    of the bench workload.  Returns (solves/s, threads, seconds)."""
+    import numpy as np
+    import gik_b200
+    from oracle import c_oracle
+    c_oracle.build()
+    tc = gik_b200.nextage_table().to_c()
+    threads = os.cpu_count() or 1
+    P = host_poses(n_sample, seed)
+    c_oracle.solve(tc, np.zeros((min(threads, n_sample), 15)), P[:min(threads, n_sample)])   # warm the threads
+    t0 = time.perf_counter()
+    c_oracle.solve(tc, np.zeros((n_sample, 15)), P, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, threads, dt
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU algorithm for the path.  The reference is Python on pinocchio
+    (not installable here: no wheel, no network), so the arm times the C port of its loop (oracle/), which
+    reproduces the reference's golden outputs; every step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or 16 * cores
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_solve_rate(min(n_sample, 2 * cores))
+    t_total = 0.0
+    for k in range(args.steps):
+        rate, threads, dt = cpu_solve_rate(n_sample, seed=1234 + k)
+        t_total += dt
+    value = n_sample * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(N_PER_GPU, "fp64 on CPU"),
+                   "sample_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} problems of the workload per step x {args.steps} steps, C oracle "
+                                   f"(Jacobi-SVD pinv, -O3 -march=native, OpenMP {threads} threads)"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._halt = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    self.samples.append(float(f[0])); self.sm_max = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+                if self._halt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._halt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import gik_b200
+    from gik_b200 import dist as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    esz = 4 if args.dtype == "f32" else 8
+    n = args.n
+    n_total = n * world
+
+    solver = gik_b200.GraspIK(gik_b200.nextage_table(), dev)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    lo = torch.tensor(WORKSPACE_LO, device=dev, dtype=dtype)
+    hi = torch.tensor(WORKSPACE_HI, device=dev, dtype=dtype)
+    pos = lo + torch.rand((n, 3), device=dev, dtype=dtype, generator=g) * (hi - lo)
+    pose_rows = torch.cat([torch.eye(3, device=dev, dtype=dtype).reshape(1, 9).expand(n, 9), pos], 1).contiguous()
+    pose = pose_rows.t().contiguous()                       # SoA [12][n]
+    q0 = torch.zeros((15, n), device=dev, dtype=dtype)      # SoA [15][n]
+    out = (torch.empty_like(q0), torch.empty(n, dtype=torch.uint8, device=dev),
+           torch.empty(n, dtype=torch.int32, device=dev), torch.empty((2, n), dtype=dtype, device=dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step():
+        flush.fill_(1)                                       # L2 flush between iterations
+        q, conv, iters, resid = solver.solve_soa(q0, pose, out=out)
+        if world > 1:
+            return gdist.all_gather_results(q, conv, n_total)
+        return q, conv
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+
+    # kernel-only events (on the launching stream = torch's current stream) for the roofline
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = solver.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        flush.fill_(1)
+        kev[k][0].record()
+        q, conv, iters, resid = solver.solve_soa(q0, pose, out=out)
+        kev[k][1].record()
+        if world > 1:
+            gdist.all_gather_results(q, conv, n_total)
+    e1.record()
+    barrier()
+    if sampler:
+        sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / max(args.steps, 1)
+    launches = solver.launches - launches0
+    t = torch.tensor([ms_total, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kernel_ms = t.tolist()
+    ms_per_step = ms_total / max(args.steps, 1)
+
+    conv_frac = out[1].float().mean()
+    iters_sum = out[2].sum(dtype=torch.int64)
+    stats = torch.stack([conv_frac.double(), iters_sum.double()])
+    if world > 1:
+        dist.all_reduce(stats)
+        stats[0] /= world
+    conv_frac, iters_sum = stats.tolist()
+
+    # ---- e2e: public batched API with pinned HOST buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        q_host = torch.zeros((n, 15), dtype=dtype).pin_memory()
+        pose_host = pose_rows.cpu().pin_memory()
+        q_res = torch.empty((n, 15), dtype=dtype).pin_memory()
+        c_res = torch.empty((n,), dtype=torch.bool).pin_memory()
+
+        def e2e_step():
+            qd = q_host.to(dev, non_blocking=True)
+            pd = pose_host.to(dev, non_blocking=True)
+            qq, cc = gik_b200.computeqgrasppose_batch(solver, qd, pd, dtype=dtype)
+            q_res.copy_(qq, non_blocking=True)
+            c_res.copy_(cc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return bool(c_res[0])
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        a1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        te = torch.tensor([max(a0.elapsed_time(a1), wall)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total * args.steps / (te.item() * 1e-3), "unit": "solves/s",
+               "h2d_bytes_per_step": int(n * (15 + 12) * esz), "d2h_bytes_per_step": int(n * (15 * esz + 1)),
+               "api": "computeqgrasppose_batch (pinned host row-major in/out)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (gik_solve_kernel): CUDA-core FMA pipe, peak measured in this run
+    fpi = gik_b200.flops_per_iter()
+    peak = gik_b200.fma_peak_tflops(local, esz)
+    iters_per_launch = iters_sum / world
+    achieved = iters_per_launch * fpi / (kernel_ms * 1e-3) * 1e-12
+    bytes_algo = gik_b200.bytes_per_solve(esz) * n
+    import json as _json
+    hbm_peak = None
+    try:
+        hbm_peak = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = _json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.dtype)
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp32" if esz == 4 else "fp64", "kernel": "gik_solve_kernel",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "peak_source": "measured in this run: register-resident FMA chains on every SM (gik_measure_fma_peak); "
+                       "MEASURED_PEAKS.json has no CUDA-core figure",
+        "flops_per_iteration": fpi, "iterations_per_launch": iters_per_launch, "kernel_ms": kernel_ms,
+        "traffic": traffic,
+        "hbm": {"algorithmic_bytes_per_launch": bytes_algo,
+                "achieved_gbs": bytes_algo / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
+                "frac": (bytes_algo / (kernel_ms * 1e-3) * 1e-9 / hbm_peak) if hbm_peak else None},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        n_sample = args.cpu_sample or 256 * cores
+        rate, threads, secs = cpu_solve_rate(n_sample)
+        cpu = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
+               "sample": f"{n_sample} problems of the same workload ({secs:.1f} s), C oracle (Jacobi-SVD pinv, -O3 "
+                         f"-march=native, OpenMP {threads} threads); the Python+pinocchio reference cannot be installed here"}
+
+    line = {
+        "metric": METRIC, "value": n_total * args.steps / (ms_total * 1e-3), "unit": "solves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(n, "fp32" if esz == 4 else "fp64"), "problems_per_gpu": n,
+                   "l2": "256 MB flush write before every step (inside the timed region)",
+                   "collective": "all_gather of q [15][n] + converged [n] per step" if world > 1 else "none",
+                   "converged_fraction": conv_frac, "mean_iterations": iters_sum / n_total},
+        "converged_solves_per_s": conv_frac * n_total * args.steps / (ms_total * 1e-3),
+        "clocks": sampler.summary() if sampler else None,
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -355,3 +355,59 @@ GIK_HD void frame_jacobians(const DevTable<T>& tab, const T (&q)[kActive], T (&A
 }
 
 }  // namespace gik
+
+// ------------------------------------------------------------------------------------------------------
+// SE3 interpolation for the edge march: pin.SE3.Interpolate(A, B, alpha) = A * exp6(alpha * log6(A^-1 B))
+// (path.py:141).  Poses are 12-vectors: rotation row-major (9) + translation (3).
+// ------------------------------------------------------------------------------------------------------
+namespace gik {
+
+// xi = log6(A^-1 B)
+template <typename T>
+GIK_HD void se3_delta(const T (&A)[12], const T (&Bp)[12], T (&xi)[6]) {
+  T R[9], p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[3 * r + c] = A[r] * Bp[c] + A[3 + r] * Bp[3 + c] + A[6 + r] * Bp[6 + c];
+    p[r] = A[r] * (Bp[9] - A[9]) + A[3 + r] * (Bp[10] - A[10]) + A[6 + r] * (Bp[11] - A[11]);
+  }
+  log6(R, p, xi);
+}
+
+// out = A * exp6(alpha * xi)
+template <typename T>
+GIK_HD void se3_advance(const T (&A)[12], const T (&xi)[6], T alpha, T (&out)[12]) {
+  const T vx = alpha * xi[0], vy = alpha * xi[1], vz = alpha * xi[2];
+  const T wx = alpha * xi[3], wy = alpha * xi[4], wz = alpha * xi[5];
+  const T t2 = wx * wx + wy * wy + wz * wz;
+  T a, b, c;  // sin(t)/t, (1-cos t)/t^2, (t - sin t)/t^3
+  if (t2 < Num<T>::kSeriesT2) {
+    a = T(1) - t2 * (T(1.0 / 6) - t2 * (T(1.0 / 120) - t2 * (T(1.0 / 5040) - t2 * T(1.0 / 362880))));
+    b = T(0.5) - t2 * (T(1.0 / 24) - t2 * (T(1.0 / 720) - t2 * (T(1.0 / 40320) - t2 * T(1.0 / 3628800))));
+    c = T(1.0 / 6) - t2 * (T(1.0 / 120) - t2 * (T(1.0 / 5040) - t2 * (T(1.0 / 362880) - t2 * T(1.0 / 39916800))));
+  } else {
+    const T t = sqrt_(t2);
+    T st, ct;
+    sincos_<false>(t, st, ct);
+    a = st / t; b = (T(1) - ct) / t2; c = (t - st) / (t2 * t);
+  }
+  // E = I + a W + b W^2 ; V = I + b W + c W^2 ; W^2 = w w^T - t2 I
+  T E[9], d[3];
+  E[0] = T(1) + b * (wx * wx - t2); E[1] = -a * wz + b * wx * wy;       E[2] = a * wy + b * wx * wz;
+  E[3] = a * wz + b * wx * wy;      E[4] = T(1) + b * (wy * wy - t2);   E[5] = -a * wx + b * wy * wz;
+  E[6] = -a * wy + b * wx * wz;     E[7] = a * wx + b * wy * wz;        E[8] = T(1) + b * (wz * wz - t2);
+  const T wv = wx * vx + wy * vy + wz * vz;
+  d[0] = vx + b * (wy * vz - wz * vy) + c * (wx * wv - t2 * vx);
+  d[1] = vy + b * (wz * vx - wx * vz) + c * (wy * wv - t2 * vy);
+  d[2] = vz + b * (wx * vy - wy * vx) + c * (wz * wv - t2 * vz);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      out[3 * r + cc] = A[3 * r] * E[cc] + A[3 * r + 1] * E[3 + cc] + A[3 * r + 2] * E[6 + cc];
+    out[9 + r] = A[9 + r] + A[3 * r] * d[0] + A[3 * r + 1] * d[1] + A[3 * r + 2] * d[2];
+  }
+}
+
+}  // namespace gik

@@ -1,0 +1,574 @@
+// gik_kernels.cu -- sm_100a kernels and the C ABI of include/gik.h.
+//
+// Mapping (DESIGN.md "Execution model"): ONE IK PROBLEM PER LANE, all state in registers, no shared memory
+// and no cross-lane traffic inside an iteration, so every issue slot of the descent loop is FP32/FP64
+// arithmetic.  The kernels are persistent: a warp owns an interleaved set of 32-problem chunks and a lane
+// whose problem finished (converged or iteration cap) stores its result and immediately pulls the next
+// problem of its warp, so the bimodal iteration count (~740 converged vs 1000 exhausted) does not idle lanes.
+// The kinematic table travels as a __grid_constant__ kernel parameter (constant bank 0): FMAs read it as
+// c[0x0][...] operands, and a handle stays immutable and stream-safe.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <new>
+
+#include "gik_table.h"
+
+namespace gik {
+
+#ifndef GIK_THREADS
+#define GIK_THREADS 128
+#endif
+#ifndef GIK_MINB_F32
+#define GIK_MINB_F32 4   // 4 x 128 threads / SM -> <= 128 registers per thread
+#endif
+#ifndef GIK_MINB_F64
+#define GIK_MINB_F64 2   // 2 x 128 threads / SM -> <= 255 registers per thread
+#endif
+
+template <typename T> struct Launch;
+template <> struct Launch<float>  { static constexpr int kMinBlocks = GIK_MINB_F32; };
+template <> struct Launch<double> { static constexpr int kMinBlocks = GIK_MINB_F64; };
+
+enum { MODE_BATCH = 0, MODE_EDGES = 1 };
+
+template <typename T>
+struct SolveArgs {
+  // batch mode
+  const T* q_init;      // [nq][n]
+  const T* pose;        // [12][n]   (edges: pose_a)
+  T* q_out;             // [nq][n]   (edges: q_path [max_steps][nq][n])
+  uint8_t* conv;        // [n]
+  int32_t* iters;       // [n] or null (edges: iters_total)
+  T* resid;             // [2][n] or null
+  // edge mode
+  const T* pose_b;      // [12][n]
+  const int32_t* num_steps;
+  int32_t* n_valid;
+  int32_t max_steps;
+  // common
+  int64_t n;
+  T eps, dt, lambda;
+  int32_t max_iters;
+  int32_t lanes;        // problems per warp kept in flight (1..32); < 32 spreads a small batch over more SMs
+};
+
+template <typename T>
+__device__ __forceinline__ void load_cube(const T* pose, int64_t n, int64_t idx, T (&cube)[12]) {
+#pragma unroll
+  for (int c = 0; c < 12; ++c) cube[c] = __ldg(pose + (int64_t)c * n + idx);
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(GIK_THREADS, Launch<T>::kMinBlocks)
+gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n = a.n;
+  const int L = a.lanes;
+  const bool enabled = lane < L;
+
+  T q[kActive], tgt[2][12];
+#pragma unroll
+  for (int i = 0; i < kActive; ++i) q[i] = T(0);
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int c = 0; c < 12; ++c) tgt[h][c] = (c % 4 == 0 && c < 9) ? T(1) : T(0);
+
+  int64_t seq = 0;      // problems handed out to this warp so far (warp-uniform)
+  int64_t idx = -1;     // problem (or edge) this lane works on
+  bool active = false;
+  int it = 0;
+  // edge mode state
+  int step = 0, nsteps = 0, it_total = 0;
+
+  for (;;) {
+    // ---------------- refill: lanes without work pull the next problem of this warp ----------------
+    const unsigned need = __ballot_sync(0xffffffffu, enabled && !active);
+    if (need) {
+      if (enabled && !active) {
+        const int64_t s = seq + __popc(need & ((1u << lane) - 1u));
+        const int64_t chunk = s / L;
+        const int64_t cand = (chunk * n_warps + warp) * L + (s - chunk * L);
+        if (cand < n) {
+          idx = cand;
+          active = true;
+          it = 0;
+#pragma unroll
+          for (int i = 0; i < kActive; ++i) q[i] = __ldg(a.q_init + (int64_t)tab.act_q[i] * n + idx);
+          T cube[12];
+          load_cube(a.pose, n, idx, cube);
+          if (MODE == MODE_EDGES) {
+            nsteps = __ldg(a.num_steps + idx);
+            step = 1;
+            it_total = 0;
+            T cb[12], xi[6], ca[12];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) ca[c] = cube[c];
+            load_cube(a.pose_b, n, idx, cb);
+            se3_delta(ca, cb, xi);
+            se3_advance(ca, xi, T(1) / T(nsteps), cube);
+            if (nsteps < 1) {  // nothing to march: reference loop body never runs (path.py:137)
+              a.n_valid[idx] = 0;
+              if (a.iters) a.iters[idx] = 0;
+              active = false;
+            }
+          }
+          hook_target(tab.arm[0], cube, tgt[0]);
+          hook_target(tab.arm[1], cube, tgt[1]);
+        }
+      }
+      seq += __popc(need);
+      if (!__any_sync(0xffffffffu, active)) break;
+    }
+
+    // ---------------- one descent iteration for every lane ----------------
+    T dq[kActive], rL, rR;
+    ik_iteration<T, true>(tab, q, tgt, a.lambda, dq, rL, rR);
+    const bool ok = (rL < a.eps) && (rR < a.eps) && (it < a.max_iters);
+    const bool done = ok || (it >= a.max_iters);
+
+    if (!done) {
+      apply_step(tab, q, dq, a.dt);
+      ++it;
+    } else if (active) {
+      // ---------------- rare path: this lane's problem ended ----------------
+      if (MODE == MODE_BATCH) {
+#pragma unroll
+        for (int i = 0; i < kActive; ++i) a.q_out[(int64_t)tab.act_q[i] * n + idx] = q[i];
+        for (int p = 0; p < tab.n_passive; ++p) {
+          const int j = tab.passive_q[p];
+          T v = __ldg(a.q_init + (int64_t)j * n + idx);
+          if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
+          a.q_out[(int64_t)j * n + idx] = v;
+        }
+        a.conv[idx] = ok ? 1 : 0;
+        if (a.iters) a.iters[idx] = it;
+        if (a.resid) { a.resid[idx] = rL; a.resid[n + idx] = rR; }
+        active = false;
+      } else {
+        it_total += it;
+        if (ok) {
+          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n;
+#pragma unroll
+          for (int i = 0; i < kActive; ++i) dst[(int64_t)tab.act_q[i] * n + idx] = q[i];
+          for (int p = 0; p < tab.n_passive; ++p) {
+            const int j = tab.passive_q[p];
+            // passive joints: clamped once any update has been applied on this edge
+            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
+            dst[(int64_t)j * n + idx] = v;
+          }
+        }
+        if (ok && step < nsteps) {
+          ++step;
+          it = 0;
+          T ca[12], cb[12], xi[6], cube[12];
+          load_cube(a.pose, n, idx, ca);
+          load_cube(a.pose_b, n, idx, cb);
+          se3_delta(ca, cb, xi);
+          se3_advance(ca, xi, T(step) / T(nsteps), cube);
+          hook_target(tab.arm[0], cube, tgt[0]);
+          hook_target(tab.arm[1], cube, tgt[1]);
+        } else {
+          a.n_valid[idx] = ok ? step : step - 1;
+          if (a.iters) a.iters[idx] = it_total;
+          active = false;
+        }
+      }
+    }
+  }
+}
+
+// ---------------- K1 / K2: forward kinematics and LOCAL frame Jacobians (parity entries) ----------------
+template <typename T>
+__global__ void __launch_bounds__(128) gik_fk_kernel(const __grid_constant__ DevTable<T> tab, int64_t n,
+                                                     const T* __restrict__ q, T* __restrict__ frames) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T qa[kActive], fr[2][12];
+#pragma unroll
+    for (int k = 0; k < kActive; ++k) qa[k] = q[(int64_t)tab.act_q[k] * n + i];
+    fk_frames<T, true>(tab, qa, fr);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 12; ++c) frames[((int64_t)h * 12 + c) * n + i] = fr[h][c];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) gik_jac_kernel(const __grid_constant__ DevTable<T> tab, int64_t n,
+                                                      const T* __restrict__ q, T* __restrict__ jac) {
+  const int nq = tab.nq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T qa[kActive], AL[6][7], AR[6][7];
+#pragma unroll
+    for (int k = 0; k < kActive; ++k) qa[k] = q[(int64_t)tab.act_q[k] * n + i];
+    frame_jacobians<T, true>(tab, qa, AL, AR);
+    for (int r = 0; r < 12 * nq; ++r) jac[(int64_t)r * n + i] = T(0);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        jac[((int64_t)r * nq + tab.act_q[k == 0 ? 0 : k]) * n + i] = AL[r][k];
+        jac[((int64_t)(6 + r) * nq + tab.act_q[k == 0 ? 0 : 6 + k]) * n + i] = AR[r][k];
+      }
+  }
+}
+
+// ---------------- K4: best-of-restarts, one warp per placement ----------------
+template <typename T>
+__global__ void __launch_bounds__(128) gik_best_of_kernel(int nq, int64_t n_place, int n_restart,
+                                                          const T* __restrict__ q,
+                                                          const uint8_t* __restrict__ conv,
+                                                          const T* __restrict__ resid, T* __restrict__ q_best,
+                                                          uint8_t* __restrict__ conv_best,
+                                                          int32_t* __restrict__ which) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = n_place * n_restart;
+  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_place;
+       p += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    // key: (not converged, max residual, restart index) -- lexicographic minimum
+    int best_r = -1; int best_nc = 2; T best_m = T(0);
+    for (int r = lane; r < n_restart; r += 32) {
+      const int64_t i = p * n_restart + r;
+      const int nc = conv[i] ? 0 : 1;
+      T m = max_(resid[i], resid[n + i]);
+      if (!(m == m)) m = T(INFINITY);  // NaN residual ranks last
+      if (best_r < 0 || nc < best_nc || (nc == best_nc && m < best_m)) { best_r = r; best_nc = nc; best_m = m; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int orr = __shfl_xor_sync(0xffffffffu, best_r, o);
+      const int onc = __shfl_xor_sync(0xffffffffu, best_nc, o);
+      const T om = __shfl_xor_sync(0xffffffffu, best_m, o);
+      const bool take = orr >= 0 && (best_r < 0 || onc < best_nc ||
+                                     (onc == best_nc && (om < best_m || (om == best_m && orr < best_r))));
+      if (take) { best_r = orr; best_nc = onc; best_m = om; }
+    }
+    const int64_t src = p * n_restart + best_r;
+    for (int j = lane; j < nq; j += 32) q_best[(int64_t)j * n_place + p] = q[(int64_t)j * n + src];
+    if (lane == 0) {
+      conv_best[p] = best_nc == 0 ? 1 : 0;
+      if (which) which[p] = best_r;
+    }
+  }
+}
+
+// ---------------- FMA roofline microbenchmark: 8 independent register-resident chains per thread ----------
+template <typename T>
+__global__ void __launch_bounds__(256) gik_fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x0 = T(threadIdx.x) * T(1e-3), x1 = x0 + T(1), x2 = x0 + T(2), x3 = x0 + T(3);
+  T x4 = x0 + T(4), x5 = x0 + T(5), x6 = x0 + T(6), x7 = x0 + T(7);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+      x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+  }
+  const T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == T(123456789)) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace gik
+
+// ========================================================================================================
+// C ABI
+// ========================================================================================================
+using namespace gik;
+
+struct gik_handle_s {
+  uint32_t magic;
+  int device;
+  int sm_count;
+  gik_table_t host;
+  DevTable<float> tab32;
+  DevTable<double> tab64;
+};
+static constexpr uint32_t kMagic = 0x67696b31u;  // "gik1"
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMagic; }
+
+inline int check_params(const gik_params_t* p) {
+  if (!p) return GIK_E_NULL;
+  if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 || p->flags != 0)
+    return GIK_E_PARAM;
+  return GIK_OK;
+}
+
+template <typename T> const DevTable<T>& table_of(gik_handle_t h);
+template <> const DevTable<float>& table_of<float>(gik_handle_t h) { return h->tab32; }
+template <> const DevTable<double>& table_of<double>(gik_handle_t h) { return h->tab64; }
+
+// Grid for the persistent solver: resident blocks per SM x SM count, shrunk for small batches; `lanes` < 32
+// spreads a batch that cannot fill the machine over more warps (one warp instruction costs the same issue
+// slot whether 1 or 32 lanes are live, so idle SM sub-partitions are the more expensive waste).
+template <typename T, int MODE>
+int solve_dims(gik_handle_t h, int64_t n, int* blocks, int* lanes) {
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gik_solve_kernel<T, MODE>, GIK_THREADS, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) occ = 1;
+  const int64_t warps_per_block = GIK_THREADS / 32;
+  const int64_t max_blocks = (int64_t)h->sm_count * occ;
+  const int64_t max_warps = max_blocks * warps_per_block;
+  int L = 32;
+  if (n < max_warps * 32) {
+    L = (int)((n + max_warps - 1) / max_warps);
+    if (L < 1) L = 1;
+    if (L > 32) L = 32;
+  }
+  int64_t warps = (n + L - 1) / L;
+  int64_t b = (warps + warps_per_block - 1) / warps_per_block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  *blocks = (int)b;
+  *lanes = L;
+  return GIK_OK;
+}
+
+template <typename T, int MODE>
+int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void* stream) {
+  a.eps = (T)prm->eps;
+  a.dt = (T)prm->dt;
+  a.lambda = (T)prm->damping;
+  a.max_iters = prm->max_iters;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  int blocks = 0, lanes = 32;
+  int rc = solve_dims<T, MODE>(h, a.n, &blocks, &lanes);
+  if (rc) return rc;
+  a.lanes = lanes;
+  gik_solve_kernel<T, MODE><<<blocks, GIK_THREADS, 0, (cudaStream_t)stream>>>(table_of<T>(h), a);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int solve_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, T* q_out,
+              uint8_t* conv, int32_t* iters, T* resid, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0) return GIK_E_SIZE;
+  int rc = check_params(prm);
+  if (rc) return rc;
+  if (n == 0) return GIK_OK;
+  if (!q_init || !pose || !q_out || !conv) return GIK_E_NULL;
+  SolveArgs<T> a{};
+  a.q_init = q_init; a.pose = pose; a.q_out = q_out; a.conv = conv; a.iters = iters; a.resid = resid;
+  a.n = n;
+  return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+}
+
+template <typename T>
+int edges_api(gik_handle_t h, int64_t n, int32_t max_steps, const T* q_start, const T* pose_a, const T* pose_b,
+              const int32_t* num_steps, const gik_params_t* prm, T* q_path, int32_t* n_valid,
+              int32_t* iters_total, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0 || max_steps < 0) return GIK_E_SIZE;
+  int rc = check_params(prm);
+  if (rc) return rc;
+  if (n == 0) return GIK_OK;
+  if (!q_start || !pose_a || !pose_b || !num_steps || !q_path || !n_valid) return GIK_E_NULL;
+  SolveArgs<T> a{};
+  a.q_init = q_start; a.pose = pose_a; a.pose_b = pose_b; a.num_steps = num_steps; a.q_out = q_path;
+  a.n_valid = n_valid; a.iters = iters_total; a.max_steps = max_steps; a.n = n;
+  return launch_solve<T, MODE_EDGES>(h, a, prm, stream);
+}
+
+template <typename T>
+int fk_api(gik_handle_t h, int64_t n, const T* q, T* frames, void* stream, bool jac) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0) return GIK_E_SIZE;
+  if (n == 0) return GIK_OK;
+  if (!q || !frames) return GIK_E_NULL;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  int64_t blocks = (n + 127) / 128;
+  if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+  if (jac) gik_jac_kernel<T><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(table_of<T>(h), n, q, frames);
+  else gik_fk_kernel<T><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(table_of<T>(h), n, q, frames);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int best_of_api(gik_handle_t h, int64_t n_place, int32_t n_restart, const T* q, const uint8_t* conv,
+                const T* resid, T* q_best, uint8_t* conv_best, int32_t* which, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n_place < 0 || n_restart < 1) return GIK_E_SIZE;
+  if (n_place == 0) return GIK_OK;
+  if (!q || !conv || !resid || !q_best || !conv_best) return GIK_E_NULL;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  int64_t blocks = (n_place + 3) / 4;
+  if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+  gik_best_of_kernel<T><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(h->host.nq, n_place, n_restart, q, conv,
+                                                                       resid, q_best, conv_best, which);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int fma_peak(int device, int repeats, double* tflops) {
+  DeviceGuard g(device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  T* out = nullptr;
+  if ((e = cudaMalloc(&out, sizeof(T))) != cudaSuccess) return (int)e;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; ++r) {
+    cudaEventRecord(e0);
+    gik_fma_peak_kernel<T><<<blocks, threads>>>(out, iters, (T)0.999, (T)0.001);
+    cudaEventRecord(e1);
+    if ((e = cudaEventSynchronize(e1)) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (r > 0 && ms > 0.f && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e != cudaSuccess) return (int)e;
+  *tflops = best * 1e-12;
+  return GIK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gik_default_params(gik_params_t* p) {
+  if (!p) return;
+  p->eps = 1e-3; p->dt = 1e-2; p->damping = 0.0; p->max_iters = 1000; p->flags = 0;
+}
+
+int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out) {
+  if (!host_table || !out) return GIK_E_NULL;
+  *out = nullptr;
+  gik_handle_s* h = new (std::nothrow) gik_handle_s();
+  if (!h) return (int)cudaErrorMemoryAllocation;
+  h->host = *host_table;
+  int rc = build_dev_table<float>(*host_table, h->tab32);
+  if (rc == GIK_OK) rc = build_dev_table<double>(*host_table, h->tab64);
+  if (rc != GIK_OK) { delete h; return rc; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) { delete h; return (int)e; }
+  if (device < 0 || device >= count) { delete h; return (int)cudaErrorInvalidDevice; }
+  e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) { delete h; return (int)e; }
+  h->device = device;
+  h->magic = kMagic;
+  *out = h;
+  return GIK_OK;
+}
+
+int gik_destroy(gik_handle_t h) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  h->magic = 0;
+  delete h;
+  return GIK_OK;
+}
+
+int gik_fk_f32(gik_handle_t h, int64_t n, const float* q, float* frames, void* s) { return fk_api<float>(h, n, q, frames, s, false); }
+int gik_fk_f64(gik_handle_t h, int64_t n, const double* q, double* frames, void* s) { return fk_api<double>(h, n, q, frames, s, false); }
+int gik_jac_f32(gik_handle_t h, int64_t n, const float* q, float* jac, void* s) { return fk_api<float>(h, n, q, jac, s, true); }
+int gik_jac_f64(gik_handle_t h, int64_t n, const double* q, double* jac, void* s) { return fk_api<double>(h, n, q, jac, s, true); }
+
+int gik_solve_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p,
+                  float* q_out, uint8_t* conv, int32_t* iters, float* resid, void* s) {
+  return solve_api<float>(h, n, q_init, pose, p, q_out, conv, iters, resid, s);
+}
+int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p,
+                  double* q_out, uint8_t* conv, int32_t* iters, double* resid, void* s) {
+  return solve_api<double>(h, n, q_init, pose, p, q_out, conv, iters, resid, s);
+}
+
+int gik_best_of_f32(gik_handle_t h, int64_t n_place, int32_t n_restart, const float* q, const uint8_t* conv,
+                    const float* resid, float* q_best, uint8_t* conv_best, int32_t* which, void* s) {
+  return best_of_api<float>(h, n_place, n_restart, q, conv, resid, q_best, conv_best, which, s);
+}
+int gik_best_of_f64(gik_handle_t h, int64_t n_place, int32_t n_restart, const double* q, const uint8_t* conv,
+                    const double* resid, double* q_best, uint8_t* conv_best, int32_t* which, void* s) {
+  return best_of_api<double>(h, n_place, n_restart, q, conv, resid, q_best, conv_best, which, s);
+}
+
+int gik_project_edges_f32(gik_handle_t h, int64_t n_edges, int32_t max_steps, const float* q_start,
+                          const float* pose_a, const float* pose_b, const int32_t* num_steps,
+                          const gik_params_t* p, float* q_path, int32_t* n_valid, int32_t* iters_total, void* s) {
+  return edges_api<float>(h, n_edges, max_steps, q_start, pose_a, pose_b, num_steps, p, q_path, n_valid, iters_total, s);
+}
+int gik_project_edges_f64(gik_handle_t h, int64_t n_edges, int32_t max_steps, const double* q_start,
+                          const double* pose_a, const double* pose_b, const int32_t* num_steps,
+                          const gik_params_t* p, double* q_path, int32_t* n_valid, int32_t* iters_total, void* s) {
+  return edges_api<double>(h, n_edges, max_steps, q_start, pose_a, pose_b, num_steps, p, q_path, n_valid, iters_total, s);
+}
+
+// SURVEY.md 8(d) breakdown, frozen: FK 540 + pose errors 250 + LOCAL Jacobians 588 + Gram 594 + Cholesky 650 +
+// triangular solves 288 + J^T z 155 + update/clamp 52.
+size_t gik_flops_per_iter(void) { return 540 + 250 + 588 + 594 + 650 + 288 + 155 + 52; }
+
+// in: q_init (nq) + pose (12); out: q (nq) + flag (1 B) + iters (4 B) + resid (2).  nq = 15.
+size_t gik_bytes_per_solve(int elem_size) { return (size_t)elem_size * (15 + 12 + 15 + 2) + 1 + 4; }
+
+int gik_measure_fma_peak(int device, int elem_size, int repeats, double* tflops) {
+  if (!tflops) return GIK_E_NULL;
+  if (repeats < 1) return GIK_E_SIZE;
+  if (elem_size == 4) return fma_peak<float>(device, repeats, tflops);
+  if (elem_size == 8) return fma_peak<double>(device, repeats, tflops);
+  return GIK_E_PARAM;
+}
+
+int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blocks, int32_t* threads) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (!blocks || !threads) return GIK_E_NULL;
+  if (n < 0) return GIK_E_SIZE;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  int b = 0, l = 32, rc;
+  if (elem_size == 4) rc = solve_dims<float, MODE_BATCH>(h, n, &b, &l);
+  else if (elem_size == 8) rc = solve_dims<double, MODE_BATCH>(h, n, &b, &l);
+  else return GIK_E_PARAM;
+  if (rc) return rc;
+  *blocks = b; *threads = GIK_THREADS;
+  return GIK_OK;
+}
+
+const char* gik_strerror(int code) {
+  switch (code) {
+    case GIK_OK: return "ok";
+    case GIK_E_NULL: return "null pointer argument";
+    case GIK_E_SIZE: return "invalid size";
+    case GIK_E_MODEL: return "kinematic table is not a tree of 1-dof revolute joints";
+    case GIK_E_TOPOLOGY: return "kinematic table does not match the compiled torso + two 6R-arm fast path";
+    case GIK_E_PARAM: return "invalid solver parameter";
+    case GIK_E_HANDLE: return "invalid handle";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+const char* gik_version(void) { return "gik 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+"""Torch-facing wrapper of the C ABI: device memory, streams and layout conversion only -- every number is
+produced by the CUDA kernels in csrc/.  Tensors must live on the handle's CUDA device; launches go to the
+current torch stream and never synchronise."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .model import KinematicTable, nextage_table
+
+# Reference literals: EPSILON (config.py:22), DT / max_iters (inverse_geometry.py:53-54)
+EPSILON = 1e-3
+DT = 1e-2
+MAX_ITERS = 1000
+
+
+@dataclass
+class SolveInfo:
+    iters: torch.Tensor     # [B] int32, updates applied
+    resid: torch.Tensor     # [B,2] residual norms (left, right) at the returned q
+
+
+def _sfx(dtype) -> str:
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise TypeError(f"dtype must be torch.float32 or torch.float64, got {dtype}")
+
+
+def as_pose12(pose, *, dtype, device, batch=None) -> torch.Tensor:
+    """Normalise a cube placement batch to [B,12] (rotation row-major, translation).
+    Accepts [B,12], [B,4,4], [B,7] (x y z qx qy qz qw, pinocchio XYZQUAT order) or [B,3] (identity rotation,
+    the only case path.py samples: path.py:47)."""
+    t = torch.as_tensor(pose, dtype=dtype, device=device) if not torch.is_tensor(pose) else pose.to(device=device, dtype=dtype)
+    if t.dim() == 1 or (t.dim() == 2 and t.shape == (4, 4)):
+        t = t.unsqueeze(0)
+    if t.dim() == 3 and t.shape[1:] == (4, 4):
+        out = torch.cat([t[:, :3, :3].reshape(-1, 9), t[:, :3, 3]], dim=1)
+    elif t.dim() == 2 and t.shape[1] == 12:
+        out = t
+    elif t.dim() == 2 and t.shape[1] == 3:
+        eye = torch.eye(3, dtype=dtype, device=device).reshape(1, 9).expand(t.shape[0], 9)
+        out = torch.cat([eye, t], dim=1)
+    elif t.dim() == 2 and t.shape[1] == 7:
+        x, y, z, w = t[:, 3], t[:, 4], t[:, 5], t[:, 6]
+        R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                         2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                         2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1)
+        out = torch.cat([R, t[:, :3]], dim=1)
+    else:
+        raise ValueError(f"unsupported pose shape {tuple(t.shape)}")
+    if batch is not None and out.shape[0] == 1 and batch != 1:
+        out = out.expand(batch, 12)
+    return out
+
+
+class GraspIK:
+    """Handle on the flattened kinematic model living on one GPU (gik_create / gik_destroy)."""
+
+    def __init__(self, table: KinematicTable | None = None, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraspIK needs a CUDA device: there is no CPU fallback")
+        self.table = table if table is not None else nextage_table()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = _cabi.lib()
+        self._h = ctypes.c_void_p()
+        ct = self.table.to_c()
+        _cabi.check(self._lib.gik_create(ctypes.byref(ct), self.device.index, ctypes.byref(self._h)), "gik_create")
+        self.nq = self.table.nq
+        self.launches = 0   # kernels of this library launched through this handle
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.gik_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _params(self, eps, dt, max_iters, damping) -> _cabi.GikParams:
+        return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), 0)
+
+    def _chk_dev(self, *ts):
+        for t in ts:
+            if t is not None and (not t.is_cuda or t.device != self.device):
+                raise ValueError(f"tensor on {t.device}, handle on {self.device}")
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def limits(self, dtype=torch.float64):
+        return (torch.as_tensor(self.table.lower, dtype=dtype, device=self.device),
+                torch.as_tensor(self.table.upper, dtype=dtype, device=self.device))
+
+    # ------------------------------------------------------------------ SoA entry points (no copies)
+    def fk_soa(self, q_soa: torch.Tensor) -> torch.Tensor:
+        """q [nq][n] -> frames [2][12][n]  (gik_fk_*)."""
+        self._chk_dev(q_soa)
+        n = q_soa.shape[1]
+        out = torch.empty((2, 12, n), dtype=q_soa.dtype, device=self.device)
+        f = getattr(self._lib, f"gik_fk_{_sfx(q_soa.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(out), self._stream()), "gik_fk")
+        self.launches += 1
+        return out
+
+    def jac_soa(self, q_soa: torch.Tensor) -> torch.Tensor:
+        """q [nq][n] -> jac [2][6][nq][n]  (gik_jac_*)."""
+        self._chk_dev(q_soa)
+        n = q_soa.shape[1]
+        out = torch.empty((2, 6, self.nq, n), dtype=q_soa.dtype, device=self.device)
+        f = getattr(self._lib, f"gik_jac_{_sfx(q_soa.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(out), self._stream()), "gik_jac")
+        self.launches += 1
+        return out
+
+    def solve_soa(self, q_init: torch.Tensor, pose: torch.Tensor, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
+                  damping=0.0, out=None):
+        """q_init [nq][n], pose [12][n] (contiguous) -> (q [nq][n], converged u8 [n], iters i32 [n], resid [2][n]).
+        `out` may carry preallocated (q, converged, iters, resid) to keep the call allocation-free."""
+        self._chk_dev(q_init, pose)
+        if q_init.dtype != pose.dtype:
+            raise TypeError("q_init and pose must share a dtype")
+        if not (q_init.is_contiguous() and pose.is_contiguous()):
+            raise ValueError("SoA inputs must be contiguous")
+        n = q_init.shape[1]
+        if q_init.shape[0] != self.nq or pose.shape != (12, n):
+            raise ValueError(f"expected q_init [{self.nq}][n] and pose [12][n], got {tuple(q_init.shape)}, {tuple(pose.shape)}")
+        if out is None:
+            q = torch.empty_like(q_init)
+            conv = torch.empty((n,), dtype=torch.uint8, device=self.device)
+            iters = torch.empty((n,), dtype=torch.int32, device=self.device)
+            resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
+        else:
+            q, conv, iters, resid = out
+        prm = self._params(eps, dt, max_iters, damping)
+        f = getattr(self._lib, f"gik_solve_{_sfx(q_init.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(q_init), self._ptr(pose), ctypes.byref(prm), self._ptr(q),
+                      self._ptr(conv), self._ptr(iters), self._ptr(resid), self._stream()), "gik_solve")
+        if n:
+            self.launches += 1
+        return q, conv, iters, resid
+
+    def best_of_soa(self, q, conv, resid, n_place: int, n_restart: int):
+        """Problem (p, r) at column p * n_restart + r.  -> (q_best [nq][n_place], conv u8, which i32)."""
+        self._chk_dev(q, conv, resid)
+        qb = torch.empty((self.nq, n_place), dtype=q.dtype, device=self.device)
+        cb = torch.empty((n_place,), dtype=torch.uint8, device=self.device)
+        wh = torch.empty((n_place,), dtype=torch.int32, device=self.device)
+        f = getattr(self._lib, f"gik_best_of_{_sfx(q.dtype)}")
+        _cabi.check(f(self._h, n_place, n_restart, self._ptr(q), self._ptr(conv), self._ptr(resid), self._ptr(qb),
+                      self._ptr(cb), self._ptr(wh), self._stream()), "gik_best_of")
+        if n_place:
+            self.launches += 1
+        return qb, cb, wh
+
+    def project_edges_soa(self, q_start, pose_a, pose_b, num_steps, max_steps: int, *, eps=EPSILON, dt=DT,
+                          max_iters=MAX_ITERS, damping=0.0):
+        """q_start [nq][E], pose_a/b [12][E], num_steps i32 [E] -> (q_path [max_steps][nq][E], n_valid i32 [E],
+        iters_total i32 [E]).  Rows >= n_valid[e] of q_path are zero."""
+        self._chk_dev(q_start, pose_a, pose_b, num_steps)
+        E = q_start.shape[1]
+        if num_steps.dtype != torch.int32:
+            raise TypeError("num_steps must be int32")
+        path = torch.zeros((max_steps, self.nq, E), dtype=q_start.dtype, device=self.device)
+        nv = torch.empty((E,), dtype=torch.int32, device=self.device)
+        itt = torch.empty((E,), dtype=torch.int32, device=self.device)
+        prm = self._params(eps, dt, max_iters, damping)
+        f = getattr(self._lib, f"gik_project_edges_{_sfx(q_start.dtype)}")
+        _cabi.check(f(self._h, E, max_steps, self._ptr(q_start.contiguous()), self._ptr(pose_a.contiguous()),
+                      self._ptr(pose_b.contiguous()), self._ptr(num_steps.contiguous()), ctypes.byref(prm),
+                      self._ptr(path), self._ptr(nv), self._ptr(itt), self._stream()), "gik_project_edges")
+        if E:
+            self.launches += 1
+        return path, nv, itt
+
+    # ------------------------------------------------------------------ row-major convenience ([B, ...])
+    def fk(self, q: torch.Tensor):
+        """q [B,nq] -> (R [B,2,3,3], p [B,2,3]) world placements of LARM_EFF / RARM_EFF."""
+        fr = self.fk_soa(q.t().contiguous())              # [2][12][B]
+        fr = fr.permute(2, 0, 1)                          # [B,2,12]
+        return fr[:, :, :9].reshape(-1, 2, 3, 3), fr[:, :, 9:]
+
+    def jacobians(self, q: torch.Tensor):
+        """q [B,nq] -> J [B,2,6,nq] (LOCAL frame, rows [linear; angular])."""
+        return self.jac_soa(q.t().contiguous()).permute(3, 0, 1, 2)
+
+    def solve(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
+              return_info=False):
+        """q_init [B,nq] (or [nq], broadcast), pose [B,12|4x4|7|3] -> (q [B,nq], converged bool [B][, SolveInfo])."""
+        p12 = as_pose12(pose, dtype=dtype, device=self.device)
+        B = p12.shape[0]
+        qi = torch.as_tensor(q_init, device=self.device).to(dtype)
+        if qi.dim() == 1:
+            qi = qi.unsqueeze(0)
+        if qi.shape[0] == 1 and B != 1:
+            qi = qi.expand(B, self.nq)
+        elif B == 1 and qi.shape[0] != 1:
+            B = qi.shape[0]
+            p12 = p12.expand(B, 12)
+        q, conv, iters, resid = self.solve_soa(qi.t().contiguous(), p12.t().contiguous(), eps=eps, dt=dt,
+                                               max_iters=max_iters, damping=damping)
+        res = (q.t(), conv.bool())
+        if return_info:
+            res = res + (SolveInfo(iters, resid.t()),)
+        return res
+
+
+_default = {}
+
+
+def default_solver(device=None) -> GraspIK:
+    """Process-wide GraspIK for the built-in Nextage table on `device` (current CUDA device by default)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the batched grasp IK has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _default:
+        _default[idx] = GraspIK(nextage_table(), torch.device("cuda", idx))
+    return _default[idx]
+
+
+def fma_peak_tflops(device_index: int, elem_size: int, repeats: int = 5) -> float:
+    out = ctypes.c_double(0.0)
+    _cabi.check(_cabi.lib().gik_measure_fma_peak(device_index, elem_size, repeats, ctypes.byref(out)), "gik_measure_fma_peak")
+    return out.value
+
+
+def flops_per_iter() -> int:
+    return int(_cabi.lib().gik_flops_per_iter())
+
+
+def bytes_per_solve(elem_size: int) -> int:
+    return int(_cabi.lib().gik_bytes_per_solve(elem_size))

@@ -1,0 +1,164 @@
+"""Batched counterparts of the two IK call sites in the reference's `path.py`:
+
+  * `sample_cube_placement` (path.py:27-67): uniform placement in a box, IK from `robot.q0`   -> `sample_grasp_poses_batch`
+  * `project_path`         (path.py:125-163): warm-started IK along an interpolated cube edge -> `project_edges_batch`
+
+plus `project_path`, a drop-in with the reference's signature and return value for ONE edge.  The planner's tree
+logic (RRT-connect, KD-tree, path.py:186-278) is out of scope; it would call these two.  The cube-vs-scene
+collision test (path.py:51-54, 144-149) and the obstacle-distance filter (path.py:61-62) are host-side hooks the
+caller may pass in; the IK itself runs in the CUDA kernels."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .inverse_geometry import _pose_to_array, solver_for
+from .ops import DT, EPSILON, MAX_ITERS, GraspIK, as_pose12
+
+Z_MIN, Z_MAX = 1.05, 1.4          # path.py:37
+STEP_SIZE = 0.025                 # path.py:125, 203-206
+
+
+def sample_cube_placements(n, p0, p1, *, z_range=(Z_MIN, Z_MAX), device="cuda", dtype=torch.float32, generator=None):
+    """n translations uniform in the box of path.py:35-45: x, y between the two given cube translations, z in
+    `z_range`; identity rotation (path.py:47).  Returns [n,3]."""
+    p0 = np.asarray(p0, float).reshape(-1)[-3:]
+    p1 = np.asarray(p1, float).reshape(-1)[-3:]
+    lo = torch.tensor([min(p0[0], p1[0]), min(p0[1], p1[1]), z_range[0]], dtype=dtype, device=device)
+    hi = torch.tensor([max(p0[0], p1[0]), max(p0[1], p1[1]), z_range[1]], dtype=dtype, device=device)
+    u = torch.rand((n, 3), dtype=dtype, device=device, generator=generator)
+    return lo + u * (hi - lo)
+
+
+def sample_grasp_poses_batch(robot, n, cubeplacementq0, cubeplacementqgoal, *, q0=None, dtype=torch.float32,
+                             generator=None, cube_collision=None, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
+                             damping=0.0):
+    """n candidate samples of path.sample_cube_placement evaluated at once: every placement gets one IK solve
+    from `q0` (robot.q0 = zeros by default, path.py:57).  Returns (q [n,nq], placements [n,3], ok bool [n]);
+    `ok` = IK converged (and `cube_collision(placements) -> bool [n]` is False when given)."""
+    solver = solver_for(robot)
+    a = _pose_to_array(cubeplacementq0)
+    b = _pose_to_array(cubeplacementqgoal)
+    pl = sample_cube_placements(n, a[9:], b[9:], device=solver.device, dtype=dtype, generator=generator)
+    qi = torch.zeros(solver.nq, dtype=dtype, device=solver.device) if q0 is None else torch.as_tensor(q0, device=solver.device).to(dtype)
+    q, conv = solver.solve(qi, pl, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
+    if cube_collision is not None:
+        conv = conv & ~torch.as_tensor(cube_collision(pl), device=solver.device).bool()
+    return q, pl, conv
+
+
+def edge_num_steps(cube_a12: torch.Tensor, cube_b12: torch.Tensor, step_size=STEP_SIZE) -> torch.Tensor:
+    """num_steps = int(||p_a - p_b|| / step_size) + 1   (path.py:129-130)."""
+    d = (cube_a12[:, 9:].double() - cube_b12[:, 9:].double()).norm(dim=1)
+    return (torch.floor(d / step_size).to(torch.int32) + 1)
+
+
+def project_edges_batch(robot, q_start, cube_a, cube_b, *, num_steps=None, step_size=STEP_SIZE, max_steps=None,
+                        dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
+                        return_info=False):
+    """E edges marched at once.  q_start [E,nq]; cube_a / cube_b [E,12|4x4|7|3]; num_steps int [E] (default from
+    `step_size` as in the reference).  Returns (q_path [E,S,nq], n_valid int32 [E]) where q_path[e, k] is the
+    configuration for placement Interpolate(a, b, (k+1)/num_steps[e]) and n_valid[e] counts the steps before the
+    first failure (path.py:153-156); entries beyond n_valid are zero."""
+    solver = solver_for(robot)
+    dev = solver.device
+    a12 = as_pose12(cube_a, dtype=dtype, device=dev)
+    b12 = as_pose12(cube_b, dtype=dtype, device=dev, batch=a12.shape[0])
+    E = a12.shape[0]
+    qs = torch.as_tensor(q_start, device=dev).to(dtype)
+    if qs.dim() == 1:
+        qs = qs.unsqueeze(0).expand(E, solver.nq)
+    if num_steps is None:
+        ns = edge_num_steps(a12, b12, step_size)
+    else:
+        ns = torch.as_tensor(num_steps, device=dev).to(torch.int32).reshape(-1)
+        if ns.numel() == 1:
+            ns = ns.expand(E).contiguous()
+    if max_steps is None:
+        max_steps = int(ns.max().item()) if E else 0     # host sync: pass max_steps to avoid it
+    path, nv, itt = solver.project_edges_soa(qs.t().contiguous(), a12.t().contiguous(), b12.t().contiguous(),
+                                             ns.contiguous(), max_steps, eps=eps, dt=dt, max_iters=max_iters,
+                                             damping=damping)
+    out = (path.permute(2, 0, 1), nv)
+    if return_info:
+        out = out + (itt,)
+    return out
+
+
+def project_path(robot, cube, q_curr, cube_curr, cube_rand, step_size=STEP_SIZE, viz=None, *, cube_collision=None,
+                 collision=None, dtype=torch.float64):
+    """Drop-in for path.project_path (path.py:125-163), one edge: returns (robot_path, cube_path), both starting
+    with the given q / placement.  `cube_collision(pose12) -> bool` and `collision(q) -> bool` reproduce the
+    host-side tests of path.py:144-149 and inverse_geometry.py:70 when given."""
+    solver = solver_for(robot, cube)
+    a = _pose_to_array(cube_curr)
+    b = _pose_to_array(cube_rand)
+    num_steps = int(np.linalg.norm(a[9:] - b[9:]) / step_size) + 1
+    q_path, nv, = project_edges_batch(solver, np.asarray(q_curr, float), a[None], b[None], num_steps=[num_steps],
+                                      max_steps=num_steps, dtype=dtype)
+    n_ok = int(nv[0].item())
+    qs = q_path[0].double().cpu().numpy()
+    robot_path, cube_path = [q_curr], [cube_curr]
+    # placements along the edge, same interpolation as the kernel, for the returned cube_path
+    A = torch.from_numpy(a)[None]
+    B = torch.from_numpy(b)[None]
+    for k in range(n_ok):
+        pose = se3_interpolate(A, B, (k + 1) / num_steps)[0].numpy()
+        if cube_collision is not None and cube_collision(pose):
+            break
+        if collision is not None and collision(qs[k]):
+            break
+        robot_path.append(qs[k].copy())
+        cube_path.append(_like(cube_curr, pose))
+    return robot_path, cube_path
+
+
+def _like(template, pose12):
+    """Return the placement in the caller's own type when it is a pinocchio SE3, else the 12-vector."""
+    if hasattr(template, "rotation") and hasattr(template, "translation"):
+        try:
+            return type(template)(pose12[:9].reshape(3, 3).copy(), pose12[9:].copy())
+        except Exception:
+            pass
+    return pose12
+
+
+def se3_interpolate(a12: torch.Tensor, b12: torch.Tensor, alpha: float) -> torch.Tensor:
+    """pin.SE3.Interpolate(A, B, alpha) = A exp6(alpha log6(A^-1 B)) on [B,12] float64 host/device tensors
+    (bookkeeping for `project_path`'s returned cube_path; the kernel has its own copy in gik_core.cuh)."""
+    Ra, pa = a12[:, :9].reshape(-1, 3, 3), a12[:, 9:]
+    Rb, pb = b12[:, :9].reshape(-1, 3, 3), b12[:, 9:]
+    R = Ra.transpose(1, 2) @ Rb
+    p = (Ra.transpose(1, 2) @ (pb - pa).unsqueeze(-1)).squeeze(-1)
+    # log3
+    v = torch.stack([R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]], dim=1)
+    c = ((R.diagonal(dim1=1, dim2=2).sum(1) - 1) * 0.5).clamp(-1, 1)
+    s = 0.5 * v.norm(dim=1)
+    th = torch.atan2(s, c)
+    fac = torch.where(s > 1e-12, 0.5 * th / s.clamp_min(1e-300), torch.full_like(s, 0.5))
+    w = fac.unsqueeze(1) * v
+    t2 = th * th
+    small = t2 < 1e-8
+    half_cot = torch.where(small, torch.ones_like(th), 0.5 * th * (1 + c) / s.clamp_min(1e-300))
+    alpha_c = torch.where(small, 1 - t2 / 12, half_cot)
+    beta_c = torch.where(small, torch.full_like(th, 1.0 / 12), (1 - alpha_c) / t2.clamp_min(1e-300))
+    lin = alpha_c.unsqueeze(1) * p - 0.5 * torch.cross(w, p, dim=1) + (beta_c * (w * p).sum(1)).unsqueeze(1) * w
+    # exp6(alpha * [lin; w])
+    lv, lw = alpha * lin, alpha * w
+    t2 = (lw * lw).sum(1)
+    t = t2.sqrt()
+    small = t2 < 1e-8
+    ts = t.clamp_min(1e-300)
+    ca = torch.where(small, 1 - t2 / 6, torch.sin(t) / ts)
+    cb = torch.where(small, 0.5 - t2 / 24, (1 - torch.cos(t)) / ts ** 2)
+    cc = torch.where(small, 1.0 / 6 - t2 / 120, (t - torch.sin(t)) / ts ** 3)
+    W = torch.zeros((lw.shape[0], 3, 3), dtype=lw.dtype, device=lw.device)
+    W[:, 0, 1], W[:, 0, 2], W[:, 1, 0] = -lw[:, 2], lw[:, 1], lw[:, 2]
+    W[:, 1, 2], W[:, 2, 0], W[:, 2, 1] = -lw[:, 0], -lw[:, 1], lw[:, 0]
+    W2 = W @ W
+    eye = torch.eye(3, dtype=lw.dtype, device=lw.device)
+    E = eye + ca[:, None, None] * W + cb[:, None, None] * W2
+    V = eye + cb[:, None, None] * W + cc[:, None, None] * W2
+    Ro = Ra @ E
+    po = pa + (Ra @ (V @ lv.unsqueeze(-1))).squeeze(-1)
+    return torch.cat([Ro.reshape(-1, 9), po], dim=1)

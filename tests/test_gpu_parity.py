@@ -1,0 +1,313 @@
+"""GPU parity tests: the CUDA kernels, called through the C ABI (ctypes -> libgik.so), against the CPU oracle on the
+same seeded inputs, against the reference's golden vectors, and -- at BASELINE's full size -- through
+size-independent properties.  Tolerances are the north_star's: FK placements and Jacobians 1e-9 (fp64) / 1e-5
+(fp32); converged residuals below the reference tolerance EPSILON = 1e-3; success flags agree on >= 99.9 %."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_poses, rot_rpy
+
+pytestmark = pytest.mark.gpu
+EPS = 1e-3
+
+
+@pytest.fixture(scope="module")
+def solver(table):
+    import gik_b200
+    s = gik_b200.GraspIK(table, "cuda:0")
+    yield s
+    s.close()
+
+
+def _t(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda:0")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# config 1: the reference's own outputs
+# ----------------------------------------------------------------------------------------------------------
+def test_goldens_fp64(solver, golden):
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    q, ok, info = solver.solve(torch.zeros(15), _t(P), dtype=torch.float64, return_info=True)
+    assert ok.all()
+    for i, c in enumerate(golden["cases"]):
+        assert np.abs(q[i].cpu().numpy() - np.array(c["q"])).max() < 1e-9
+        assert int(info.iters[i]) == c["iterations_chart"]
+    assert (info.resid < EPS).all()
+
+
+def test_goldens_fp32(solver, golden):
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    q, ok, info = solver.solve(torch.zeros(15), _t(P), dtype=torch.float32, return_info=True)
+    assert ok.all() and (info.resid < EPS).all()
+    for i, c in enumerate(golden["cases"]):
+        assert np.abs(q[i].double().cpu().numpy() - np.array(c["q"])).max() < 1e-4
+        assert abs(int(info.iters[i]) - c["iterations_chart"]) <= 1
+
+
+def test_dropin_signature_and_semantics(golden):
+    import gik_b200
+    c = golden["cases"][0]
+    qcurrent = np.zeros(15)
+    q, success = gik_b200.computeqgrasppose(None, qcurrent, None, (np.eye(3), np.array(c["cube_p"])))
+    assert isinstance(q, np.ndarray) and q.dtype == np.float64 and q.shape == (15,) and success is True
+    assert np.abs(q - np.array(c["q"])).max() < 1e-9
+    assert not qcurrent.any()                                   # input not mutated (inverse_geometry.py:49)
+    # collision callable: colliding everywhere -> keeps iterating to the cap and reports failure (:70, :97-98)
+    q2, s2, iters, resid = gik_b200.computeqgrasppose(None, qcurrent, None, (np.eye(3), np.array(c["cube_p"])),
+                                                      collision=lambda q: True, max_iters=745, return_info=True)
+    assert s2 is False and iters == 745 and resid.max() < EPS
+    # unreachable target never raises
+    q3, s3 = gik_b200.computeqgrasppose(None, qcurrent, None, np.array([2.0, 0.0, 1.0]))
+    assert s3 is False and np.isfinite(q3).all()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K1 / K2: forward kinematics and LOCAL Jacobians
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-5)])
+def test_fk_and_jacobians_match_oracle(solver, table, table_c, c_oracle, golden, dtype, tol):
+    rng = np.random.default_rng(0)
+    Q = rng.uniform(table.lower, table.upper, size=(4099, 15))       # ragged size
+    Q[0] = 0.0
+    R, p = c_oracle.fk(table_c, Q)
+    J = c_oracle.jac(table_c, Q)
+    Rg, pg = solver.fk(_t(Q, dtype))
+    Jg = solver.jacobians(_t(Q, dtype))
+    assert np.abs(Rg.double().cpu().numpy() - R).max() < tol
+    assert np.abs(pg.double().cpu().numpy() - p).max() < tol
+    assert np.abs(Jg.double().cpu().numpy() - J).max() < tol
+    nb = golden["notebook"]["oMf_LARM_EFF_at_q0"]                    # lab_instructions.ipynb:290-293
+    assert np.abs(pg[0, 0].double().cpu().numpy() - np.array(nb["p"])).max() < max(tol, 1e-12) * 10
+    assert np.abs(Rg[0, 0].double().cpu().numpy() - np.array(nb["R"])).max() < 1e-5
+    assert Jg[:, :, :, 1:3].abs().max() == 0                         # head joints
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K3: the descent loop
+# ----------------------------------------------------------------------------------------------------------
+def _oracle_batch(c_oracle, table_c, n, seed, box="workspace", yaw=False):
+    P = make_poses(n, seed, box)
+    if yaw:
+        rng = np.random.default_rng(seed + 100)
+        for i in range(0, n, 3):
+            P[i, :9] = rot_rpy(0, 0, rng.uniform(-0.6, 0.6)).reshape(9)
+    return P, c_oracle.solve(table_c, np.zeros((n, 15)), P)
+
+
+def test_solve_fp64_matches_oracle(solver, table_c, c_oracle):
+    n = 1500                                                        # not a multiple of 32
+    P, (qo, oko, ito, ro) = _oracle_batch(c_oracle, table_c, n, 21, yaw=True)
+    q, ok, info = solver.solve(torch.zeros(15), _t(P), dtype=torch.float64, return_info=True)
+    ok = ok.cpu().numpy(); q = q.cpu().numpy()
+    assert (ok == oko).mean() >= 0.999
+    both = ok & oko
+    assert 0.3 < both.mean() < 0.95
+    assert np.abs(q[both] - qo[both]).max() < 1e-8
+    assert (info.iters.cpu().numpy()[both] == ito[both]).all()
+    assert (info.resid.cpu().numpy()[ok] < EPS).all()
+    # exhausted problems ran exactly max_iters updates (inverse_geometry.py:56)
+    assert (info.iters.cpu().numpy()[~ok] == 1000).all()
+
+
+def test_solve_fp32_matches_oracle(solver, table, table_c, c_oracle):
+    n = 4096
+    P, (qo, oko, ito, ro) = _oracle_batch(c_oracle, table_c, n, 22)
+    q, ok, info = solver.solve(torch.zeros(15), _t(P), dtype=torch.float32, return_info=True)
+    ok = ok.cpu().numpy(); q = q.double().cpu().numpy()
+    assert (ok == oko).mean() >= 0.999                               # north_star: flags agree on >= 99.9 %
+    both = ok & oko
+    assert np.abs(q[both] - qo[both]).max() < 1e-3
+    assert np.abs(info.iters.cpu().numpy()[both] - ito[both]).max() <= 2
+    assert (info.resid.cpu().numpy()[ok] < EPS).all()
+    # converged outputs re-checked in fp64 by the oracle's own residual: below the reference tolerance (+ fp32 slack)
+    Rh, ph = c_oracle.fk(table_c, q[ok])
+    from oracle import grasp_ik_np as o
+    for i in np.nonzero(ok)[0][:200]:
+        tg = o.hook_targets(P[i, :9].reshape(3, 3), P[i, 9:])
+        for h in (0, 1):
+            assert np.linalg.norm(o.hand_error(q[i], h, tg[h])) < EPS + 2e-5
+    assert (q >= table.lower - 1e-12).all() and (q <= table.upper + 1e-12).all()
+
+
+def test_reference_sampler_box(solver, table_c, c_oracle):
+    # path.py:35-37 box from robot.q0: about a third converges, the rest pin LARM/RARM_JOINT4 at their limit
+    P, (qo, oko, ito, ro) = _oracle_batch(c_oracle, table_c, 256, 23, box="sampler")
+    q, ok = solver.solve(torch.zeros(15), _t(P), dtype=torch.float64)
+    assert (ok.cpu().numpy() == oko).all()
+    assert 0.1 < oko.mean() < 0.6
+
+
+def test_warm_start_and_passive_joints(solver, table, table_c, c_oracle):
+    rng = np.random.default_rng(5)
+    n = 64
+    P = make_poses(n, 31)
+    Q0 = rng.uniform(table.lower, table.upper, size=(n, 15)) * 0.3
+    Q0[:, 1] = 2.0                                                  # head joint OUTSIDE its limit: clamped by the first update
+    qo, oko, ito, _ = c_oracle.solve(table_c, Q0, P)
+    q, ok, info = solver.solve(_t(Q0), _t(P), dtype=torch.float64, return_info=True)
+    q = q.cpu().numpy(); ok = ok.cpu().numpy()
+    assert (ok == oko).mean() >= 0.98
+    both = ok & oko
+    assert np.abs(q[both] - qo[both]).max() < 1e-8
+    moved = info.iters.cpu().numpy() > 0
+    assert np.allclose(q[moved, 1], table.upper[1]) and np.allclose(q[moved, 2], Q0[moved, 2])
+
+
+def test_edge_cases(solver, table_c, c_oracle):
+    # empty batch
+    q, ok = solver.solve(torch.zeros((0, 15)), torch.zeros((0, 12)), dtype=torch.float32)
+    assert q.shape == (0, 15) and ok.shape == (0,)
+    # single problem, max_iters = 0: loop never runs -> q unchanged, not converged
+    P = make_poses(1, 0)
+    q, ok, info = solver.solve(torch.zeros(15), _t(P), dtype=torch.float64, max_iters=0, return_info=True)
+    assert not ok.any() and int(info.iters[0]) == 0 and q.abs().max() == 0
+    # already-converged start: zero iterations and q returned bit-identical
+    P = make_poses(40, 7, "sampler")
+    q1, ok1 = solver.solve(torch.zeros(15), _t(P), dtype=torch.float64)
+    q2, ok2, info = solver.solve(q1, _t(P), dtype=torch.float64, return_info=True)
+    assert ok1.any() and (ok2[ok1]).all()
+    assert (info.iters[ok1] == 0).all() and torch.equal(q2[ok1], q1[ok1])
+    # unreachable targets stay finite
+    far = make_poses(33, 1); far[:, 9] += 3.0
+    q, ok = solver.solve(torch.zeros(15), _t(far), dtype=torch.float32)
+    assert not ok.any() and torch.isfinite(q).all()
+
+
+def test_cabi_error_codes_on_device(solver):
+    from gik_b200 import _cabi
+    lib = _cabi.lib()
+    prm = _cabi.GikParams(1e-3, 1e-2, 0.0, 1000, 0)
+    z = ctypes.c_void_p(0)
+    assert lib.gik_solve_f32(solver._h, 4, z, z, ctypes.byref(prm), z, z, z, z, z) == -1           # GIK_E_NULL
+    assert lib.gik_solve_f32(solver._h, -1, z, z, ctypes.byref(prm), z, z, z, z, z) == -2          # GIK_E_SIZE
+    bad = _cabi.GikParams(-1.0, 1e-2, 0.0, 1000, 0)
+    assert lib.gik_solve_f32(solver._h, 4, z, z, ctypes.byref(bad), z, z, z, z, z) == -5           # GIK_E_PARAM
+    assert lib.gik_solve_f32(solver._h, 0, z, z, ctypes.byref(prm), z, z, z, z, z) == 0            # n = 0 is a no-op
+    with pytest.raises(_cabi.GikError):
+        solver.solve(torch.zeros(15), torch.zeros((2, 3)), eps=0.0)
+    b, t = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.gik_solve_launch_dims(solver._h, 4, 1 << 20, ctypes.byref(b), ctypes.byref(t)) == 0
+    assert b.value % 148 == 0 and t.value == 128
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K4 / config 3: best-of restarts
+# ----------------------------------------------------------------------------------------------------------
+def test_best_of_restarts(solver):
+    import gik_b200
+    rng = np.random.default_rng(3)
+    n_place, R = 37, 8
+    n = n_place * R
+    q = torch.from_numpy(rng.normal(size=(15, n))).cuda()
+    conv = torch.from_numpy((rng.uniform(size=n) < 0.4).astype(np.uint8)).cuda()
+    conv[:R] = 0                                                     # placement 0: nothing converged
+    resid = torch.from_numpy(rng.uniform(1e-4, 1e-3, size=(2, n))).cuda()
+    resid[:, R + 2] = resid[:, R + 5]; conv[R + 2] = 1; conv[R + 5] = 1   # exact tie -> lowest index wins
+    qb, cb, wh = solver.best_of_soa(q, conv, resid, n_place, R)
+    m = resid.max(0).values.cpu().numpy().reshape(n_place, R)
+    c = conv.cpu().numpy().reshape(n_place, R).astype(bool)
+    for p in range(n_place):
+        key = np.where(c[p], m[p], np.inf) if c[p].any() else m[p]
+        exp = int(np.argmin(key))
+        assert int(wh[p]) == exp and bool(cb[p]) == bool(c[p].any())
+        assert torch.equal(qb[:, p], q[:, p * R + exp])
+    # end to end: restarts only ever add converged placements and never change restart 0's answer when it wins
+    P = make_poses(64, 41)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    q1, ok1 = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), _t(P), dtype=torch.float64)
+    q8, ok8, info = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), _t(P), dtype=torch.float64, restarts=8,
+                                                     damping=1e-6, generator=g, return_info=True)
+    assert (ok8 | ~ok1).all() and ok8.sum() >= ok1.sum()
+    assert (info.resid[ok8] < EPS).all()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# K5 / config 4: edge projection (path.project_path)
+# ----------------------------------------------------------------------------------------------------------
+def test_project_edges_matches_oracle(solver, table_c, c_oracle):
+    import gik_b200
+    E, S = 24, 6
+    A = make_poses(E, 51, "sampler"); A[:, 11] = 0.93 + 0.2 * np.random.default_rng(1).uniform(size=E)
+    B = A.copy(); B[:, 9:] += np.random.default_rng(2).uniform(-0.08, 0.08, size=(E, 3))
+    B[::4, :9] = rot_rpy(0, 0, 0.5).reshape(9)                       # some edges rotate the cube (SE3.Interpolate)
+    B[5, 11] = 2.5                                                   # this edge runs out of reach -> early stop
+    ns = np.random.default_rng(3).integers(1, S + 1, size=E).astype(np.int32)
+    q0, ok0, _, _ = c_oracle.solve(table_c, np.zeros((E, 15)), A)
+    keep = ok0
+    A, B, ns, q0 = A[keep], B[keep], ns[keep], q0[keep]
+    E = len(A)
+    assert E >= 8
+    path_o, nv_o, it_o = c_oracle.project_edges(table_c, q0, A, B, ns, S)
+    path, nv, itt = gik_b200.project_edges_batch(solver, _t(q0), _t(A), _t(B), num_steps=ns, max_steps=S,
+                                                 dtype=torch.float64, return_info=True)
+    assert np.array_equal(nv.cpu().numpy(), nv_o)
+    assert np.array_equal(itt.cpu().numpy(), it_o)
+    assert (nv_o < ns).any() and (nv_o == ns).any()
+    path = path.cpu().numpy()
+    for e in range(E):
+        assert np.abs(path[e, :nv_o[e]] - path_o[e, :nv_o[e]]).max(initial=0) < 1e-8
+        assert np.abs(path[e, nv_o[e]:]).max(initial=0) == 0
+    # fp32 variant: same step counts on all but borderline edges, same configurations to fp32 accuracy
+    path32, nv32 = gik_b200.project_edges_batch(solver, _t(q0), _t(A), _t(B), num_steps=ns, max_steps=S,
+                                                dtype=torch.float32)
+    same = nv32.cpu().numpy() == nv_o
+    assert same.mean() >= 0.9
+    for e in np.nonzero(same)[0]:
+        assert np.abs(path32[e, :nv_o[e]].double().cpu().numpy() - path_o[e, :nv_o[e]]).max(initial=0) < 2e-3
+
+
+def test_project_path_dropin(solver, golden):
+    import gik_b200
+    from oracle import grasp_ik_np as o
+    q0 = np.array(golden["cases"][0]["q"])
+    a = (np.eye(3), np.array([0.33, -0.3, 0.93])); b = (np.eye(3), np.array([0.36, -0.25, 1.0]))
+    ref = o.project_path(q0, a, b)
+    rp, cp = gik_b200.project_path(solver, None, q0, a, b)
+    assert len(rp) == len(ref) + 1 == len(cp) and rp[0] is q0
+    for k, qk in enumerate(ref):
+        assert np.abs(rp[k + 1] - qk).max() < 1e-8
+    assert np.abs(cp[-1][9:] - b[1]).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full size (BASELINE config 2: 2^20 placements, fp32): size-independent properties
+# ----------------------------------------------------------------------------------------------------------
+def test_full_size_properties_fp32(solver, table):
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo = torch.tensor([0.20, -0.40, 0.93], device="cuda"); hi = torch.tensor([0.60, 0.40, 1.40], device="cuda")
+    pos = lo + torch.rand((n, 3), device="cuda", generator=g) * (hi - lo)
+    pose = torch.cat([torch.eye(3, device="cuda").reshape(1, 9).expand(n, 9), pos], 1).t().contiguous()
+    q0 = torch.zeros((15, n), device="cuda")
+    q, conv, iters, resid = solver.solve_soa(q0, pose)
+    torch.cuda.synchronize()
+    conv_b = conv.bool()
+    frac = conv_b.float().mean().item()
+    assert 0.4 < frac < 0.9
+    # (1) converged <=> both residuals below eps; iteration counts within the cap; exhausted == cap
+    assert (resid[:, conv_b] < EPS).all() and (iters[~conv_b] == 1000).all() and (iters[conv_b] < 1000).all()
+    # (2) joint limits hold for every output
+    lo_q, hi_q = solver.limits(torch.float32)
+    assert (q >= lo_q[:, None] - 1e-6).all() and (q <= hi_q[:, None] + 1e-6).all()
+    # (3) FK of the outputs (K1) lands both hands on the hook targets of the converged problems
+    fr = solver.fk_soa(q)                                            # [2][12][n]
+    hook = torch.tensor([0.05, -0.05], device="cuda")
+    for h in (0, 1):
+        tgt = pos.t().clone(); tgt[1] += hook[h]
+        d = (fr[h, 9:12] - tgt).norm(dim=0)
+        assert d[conv_b].max() < EPS + 1e-5
+    # (4) idempotence: re-solving from the converged answer is a zero-iteration no-op
+    q2, conv2, iters2, _ = solver.solve_soa(q, pose)
+    assert (conv2.bool() | ~conv_b).all() and (iters2[conv_b] == 0).all() and torch.equal(q2[:, conv_b], q[:, conv_b])
+    # (5) results do not depend on where a problem sits in the batch (persistent-lane scheduling): bit-exact
+    perm = torch.randperm(n, device="cuda", generator=g)
+    qp, convp, itersp, _ = solver.solve_soa(q0, pose[:, perm].contiguous())
+    assert torch.equal(qp, q[:, perm]) and torch.equal(convp, conv[perm]) and torch.equal(itersp, iters[perm])
+    # (6) a slab solved alone equals the same slab inside the full batch (what multi-GPU sharding relies on)
+    a, b = n // 8, n // 4
+    qs, convs, _, _ = solver.solve_soa(q0[:, a:b].contiguous(), pose[:, a:b].contiguous())
+    assert torch.equal(qs, q[:, a:b]) and torch.equal(convs, conv[a:b])

@@ -1,0 +1,57 @@
+"""Host-side helpers of the drop-in layer (pose normalisation, SE3 interpolation bookkeeping, sharding) -- CPU."""
+import numpy as np
+import torch
+
+from conftest import rot_rpy
+
+
+def test_as_pose12_accepts_every_documented_layout():
+    import gik_b200
+    R = rot_rpy(0.1, -0.2, 0.3)
+    p = np.array([0.3, -0.1, 1.0])
+    M = np.eye(4); M[:3, :3] = R; M[:3, 3] = p
+    ref = np.concatenate([R.reshape(9), p])
+    w = np.sqrt(max(0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    quat = np.array([(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w])
+    for x in (ref, M, np.concatenate([p, quat])):
+        out = gik_b200.as_pose12(x, dtype=torch.float64, device="cpu")
+        assert out.shape == (1, 12) and np.abs(out[0].numpy() - ref).max() < 1e-12
+    out = gik_b200.as_pose12(p[None], dtype=torch.float64, device="cpu")
+    assert np.abs(out[0].numpy() - np.concatenate([np.eye(3).reshape(9), p])).max() == 0
+
+
+def test_se3_interpolate_matches_oracle(c_oracle):
+    import gik_b200
+    rng = np.random.default_rng(0)
+    A = np.zeros((16, 12)); B = np.zeros((16, 12))
+    for i in range(16):
+        A[i, :9] = rot_rpy(*rng.uniform(-1, 1, 3)).reshape(9); A[i, 9:] = rng.uniform(-1, 1, 3)
+        B[i, :9] = rot_rpy(*rng.uniform(-1, 1, 3)).reshape(9); B[i, 9:] = rng.uniform(-1, 1, 3)
+    B[0] = A[0]                                      # zero displacement
+    B[1, :9] = A[1, :9]                              # pure translation (the reference's case, path.py:47)
+    for alpha in (0.0, 0.25, 1.0):
+        ref = c_oracle.interpolate(A, B, np.full(16, alpha))
+        out = gik_b200.se3_interpolate(torch.from_numpy(A), torch.from_numpy(B), alpha).numpy()
+        assert np.abs(out - ref).max() < 1e-12
+    assert np.abs(c_oracle.interpolate(A, B, np.ones(16)) - B).max() < 1e-12
+    lerp = A[1, 9:] + 0.25 * (B[1, 9:] - A[1, 9:])
+    assert np.abs(c_oracle.interpolate(A[1:2], B[1:2], np.array([0.25]))[0, 9:] - lerp).max() < 1e-14
+
+
+def test_edge_num_steps_follows_reference_formula():
+    import gik_b200
+    a = torch.tensor([[1., 0, 0, 0, 1, 0, 0, 0, 1, 0.33, -0.3, 0.93]], dtype=torch.float64)
+    b = torch.tensor([[1., 0, 0, 0, 1, 0, 0, 0, 1, 0.33, -0.3 + 0.1, 0.93]], dtype=torch.float64)
+    assert gik_b200.edge_num_steps(a, b).tolist() == [int(0.1 / 0.025) + 1]       # path.py:129-130
+    assert gik_b200.edge_num_steps(a, a).tolist() == [1]
+
+
+def test_shard_bounds_cover_and_balance():
+    from gik_b200.dist import shard_bounds
+    for n in (0, 1, 7, 64, 1000003):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1

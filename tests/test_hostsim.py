@@ -1,0 +1,48 @@
+"""The device arithmetic (csrc/gik_core.cuh) compiled for the host, against the oracle -- CPU only.  This checks the
+kernel MATH (backward chain walk, block-structured Cholesky + Sherman-Morrison step, log6) in fp64 and fp32
+without a GPU; the `-m gpu` tests check the kernels themselves through the C ABI."""
+import numpy as np
+
+from conftest import make_poses, rot_rpy
+
+
+def test_hostsim_goldens(golden, table_c, hostsim):
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    for dt, tol in ((np.float64, 1e-9), (np.float32, 1e-4)):
+        q, ok, it, r = hostsim.solve(table_c, np.zeros((2, 15)), P, dt)
+        assert ok.all() and (r < 1e-3).all()
+        for i, c in enumerate(golden["cases"]):
+            assert np.abs(q[i] - np.array(c["q"])).max() < tol
+            assert abs(int(it[i]) - c["iterations_chart"]) <= (0 if dt == np.float64 else 1)
+
+
+def test_hostsim_fk_jac_tolerances(table, table_c, hostsim, c_oracle):
+    rng = np.random.default_rng(0)
+    Q = rng.uniform(table.lower, table.upper, size=(256, 15))
+    R, p = c_oracle.fk(table_c, Q)
+    J = c_oracle.jac(table_c, Q)
+    for dt, tol in ((np.float64, 1e-9), (np.float32, 1e-5)):   # north_star tolerances
+        R2, p2 = hostsim.fk(table_c, Q, dt)
+        J2 = hostsim.jac(table_c, Q, dt)
+        assert np.abs(R - R2).max() < tol and np.abs(p - p2).max() < tol and np.abs(J - J2).max() < tol
+
+
+def test_hostsim_solve_matches_oracle(table_c, hostsim, c_oracle):
+    P = make_poses(96, 11)
+    P[:8, :9] = rot_rpy(0, 0, 0.4).reshape(9)          # a few yawed cubes
+    qo, oko, ito, _ = c_oracle.solve(table_c, np.zeros((96, 15)), P)
+    q, ok, it, r = hostsim.solve(table_c, np.zeros((96, 15)), P, np.float64)
+    assert (ok == oko).all()
+    assert np.abs(q[oko] - qo[oko]).max() < 1e-9 and (it[oko] == ito[oko]).all()
+    q, ok, it, r = hostsim.solve(table_c, np.zeros((96, 15)), P, np.float32)
+    assert (ok == oko).mean() >= 0.97
+    both = ok & oko
+    assert np.abs(q[both] - qo[both]).max() < 1e-3 and np.abs(it[both] - ito[both]).max() <= 2
+    assert (r[ok] < 1e-3).all()
+
+
+def test_hostsim_damping_shortens_step(table_c, hostsim):
+    P = make_poses(4, 2)
+    q0, *_ = hostsim.solve(table_c, np.zeros((4, 15)), P, np.float64, max_iters=1)
+    q1, *_ = hostsim.solve(table_c, np.zeros((4, 15)), P, np.float64, max_iters=1, damping=1.0)
+    assert (np.abs(q1).sum(1) < np.abs(q0).sum(1)).all()

@@ -1,0 +1,119 @@
+"""The oracle against the reference's own golden vectors and known answers, and the C oracle
+against the numpy oracle.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import grasp_ik_np as o
+from conftest import make_poses, rot_rpy
+
+
+def test_numpy_oracle_reproduces_reference_goldens(golden):
+    for case in golden["cases"]:
+        q, ok, iters, resid = o.computeqgrasppose(np.array(golden["q_init"]), np.array(case["cube_R"]).reshape(3, 3),
+                                                  np.array(case["cube_p"]), return_info=True)
+        assert ok is True
+        assert iters == case["iterations_chart"]
+        assert np.abs(q - np.array(case["q"])).max() < 1e-12
+        assert (resid < 1e-3).all()
+
+
+def test_c_oracle_reproduces_reference_goldens(golden, table_c, c_oracle):
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    q, ok, iters, resid = c_oracle.solve(table_c, np.zeros((2, 15)), P)
+    assert ok.all()
+    assert list(iters) == [c["iterations_chart"] for c in golden["cases"]]
+    for i, c in enumerate(golden["cases"]):
+        assert np.abs(q[i] - np.array(c["q"])).max() < 1e-12
+
+
+def test_fk_known_answer_from_notebook(golden):
+    nb = golden["notebook"]["oMf_LARM_EFF_at_q0"]
+    R, p = o.hand_placement(np.zeros(15), 0)
+    assert np.abs(R - np.array(nb["R"])).max() < 1e-9      # printed with 6 significant digits
+    assert np.abs(p - np.array(nb["p"])).max() < 1e-12
+    assert o.JOINT_NAMES == golden["notebook"]["joint_names"][1:]
+    Rr, pr = o.hand_placement(np.zeros(15), 1)
+    assert np.allclose(pr, [0.452, -0.28, 0.851], atol=1e-12)
+
+
+def test_initial_error_components_match_error_charts():
+    # q0_error_charts.png intercepts: L x -0.512 y -0.320 z +0.079 yaw -1.571; R x +0.041 y +0.151 z +0.079 yaw +1.572
+    tg = o.hook_targets(*o.CUBE_PLACEMENT)
+    eL = o.hand_error(np.zeros(15), 0, tg[0])
+    eR = o.hand_error(np.zeros(15), 1, tg[1])
+    assert abs(abs(eL[5]) - 1.571) < 2e-3 and abs(abs(eR[5]) - 1.572) < 2e-3
+    assert np.linalg.norm(eL[:3]) > 0.3 and np.linalg.norm(eR[:3]) < 0.3
+
+
+def test_local_jacobian_matches_finite_differences():
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        q = rng.uniform(o.LOWER, o.UPPER)
+        for h in (0, 1):
+            J = o.frame_jacobian_local(q, h)
+            Rh, ph = o.hand_placement(q, h)
+            for k in range(15):
+                dq = np.zeros(15); dq[k] = 1e-6
+                R2, p2 = o.hand_placement(q + dq, h)
+                v = o.log6(Rh.T @ R2, Rh.T @ (p2 - ph)) / 1e-6
+                assert np.abs(v - J[:, k]).max() < 1e-4
+            assert np.abs(J[:, [1, 2]]).max() == 0.0          # head joints never move a hand
+
+
+def test_log6_properties():
+    assert np.abs(o.log6(np.eye(3), np.zeros(3))).max() == 0.0
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        w = rng.normal(size=3); w *= rng.uniform(0, 3.1) / np.linalg.norm(w)
+        th = np.linalg.norm(w)
+        K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+        e = o.log6(R, np.zeros(3))
+        assert np.abs(e[3:] - w).max() < 1e-9 and np.abs(e[:3]).max() == 0.0
+    # near pi: pinocchio's explicit branch
+    R = rot_rpy(0, 0, np.pi - 1e-3)
+    assert abs(np.linalg.norm(o.log3(R)[0]) - (np.pi - 1e-3)) < 1e-6
+
+
+def test_c_oracle_matches_numpy_oracle(table_c, c_oracle):
+    rng = np.random.default_rng(1)
+    Q = rng.uniform(o.LOWER, o.UPPER, size=(16, 15))
+    R, p = c_oracle.fk(table_c, Q)
+    J = c_oracle.jac(table_c, Q)
+    for i in range(16):
+        for h in (0, 1):
+            Rn, pn = o.hand_placement(Q[i], h)
+            assert np.abs(R[i, h] - Rn).max() < 1e-14 and np.abs(p[i, h] - pn).max() < 1e-14
+            assert np.abs(J[i, h] - o.frame_jacobian_local(Q[i], h)).max() < 1e-14
+    P = make_poses(6, 5)
+    q, ok, it, res = c_oracle.solve(table_c, np.zeros((6, 15)), P)
+    for i in range(6):
+        qn, okn, itn, rn = o.computeqgrasppose(np.zeros(15), np.eye(3), P[i, 9:], return_info=True)
+        assert okn == ok[i] and itn == it[i]
+        assert np.abs(qn - q[i]).max() < 1e-10
+
+
+def test_oracle_edge_cases(table_c, c_oracle):
+    P = make_poses(1, 0)
+    q, ok, it, _ = c_oracle.solve(table_c, np.zeros((1, 15)), P, max_iters=0)   # loop never runs
+    assert not ok[0] and it[0] == 0 and np.abs(q).max() == 0.0
+    q, ok, it, _ = c_oracle.solve(table_c, np.zeros((0, 15)), np.zeros((0, 12)))  # empty batch
+    assert q.shape == (0, 15)
+    # already converged start: zero iterations, q returned unchanged (even outside the limits' clamp path)
+    g, okg, _, _ = c_oracle.solve(table_c, np.zeros((1, 15)), P if False else make_poses(1, 7, "sampler"))
+    if okg[0]:
+        q2, ok2, it2, _ = c_oracle.solve(table_c, g, make_poses(1, 7, "sampler"))
+        assert ok2[0] and it2[0] == 0 and np.array_equal(q2, g)
+
+
+def test_project_path_oracle_consistency(table_c, c_oracle):
+    # warm-started march along one edge: C oracle == numpy oracle
+    q0, ok, _, _ = c_oracle.solve(table_c, np.zeros((1, 15)), np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 0.33, -0.3, 0.93]], float))
+    assert ok[0]
+    a = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 0.33, -0.3, 0.93]], float)
+    b = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 0.36, -0.25, 1.0]], float)
+    path, nv, itt = c_oracle.project_edges(table_c, q0, a, b, [4], 4)
+    ref = o.project_path(q0[0], (np.eye(3), a[0, 9:]), (np.eye(3), b[0, 9:]), num_steps=4)
+    assert nv[0] == len(ref) == 4
+    for k in range(4):
+        assert np.abs(path[0, k] - ref[k]).max() < 1e-10
