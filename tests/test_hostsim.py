@@ -30,6 +30,7 @@ def test_hostsim_fk_jac_tolerances(table, table_c, hostsim, c_oracle):
 def test_hostsim_solve_matches_oracle(table_c, hostsim, c_oracle):
     P = make_poses(96, 11)
     P[:8, :9] = rot_rpy(0, 0, 0.4).reshape(9)          # a few yawed cubes
+    P[:, 9] = np.minimum(P[:, 9], 0.55)                # stay clear of the near-singular rim (see test_gpu_parity._assert_q_close)
     qo, oko, ito, _ = c_oracle.solve(table_c, np.zeros((96, 15)), P)
     q, ok, it, r = hostsim.solve(table_c, np.zeros((96, 15)), P, np.float64)
     assert (ok == oko).all()
