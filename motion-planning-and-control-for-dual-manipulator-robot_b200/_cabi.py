@@ -10,7 +10,8 @@ import subprocess
 from .model import GikTable
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgik.so")
+# GIK_LIB overrides the library path (A/B runs of differently tuned builds of the SAME sources; still no fallback)
+LIB_PATH = os.environ.get("GIK_LIB") or os.path.join(_HERE, "libgik.so")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -37,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/gik_kernels.cu for sm_100a into libgik.so next to this file (nvcc cross-compiles
     without a GPU).  Rebuilds when a source is newer than the library."""
     srcs = _sources()
+    if os.environ.get("GIK_LIB"):
+        return LIB_PATH
     if not force and os.path.exists(LIB_PATH):
         t = os.path.getmtime(LIB_PATH)
         if all(os.path.getmtime(s) <= t for s in srcs if os.path.exists(s)):
