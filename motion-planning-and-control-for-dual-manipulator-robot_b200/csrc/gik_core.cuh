@@ -45,6 +45,7 @@ struct ArmConst {
   T t[7][3];    // parent -> joint translation of chain joint k
   T finv_R[9];  // (hand frame offset on the tip joint)^-1, row-major
   T finv_p[3];
+  T tip_lin[3]; // finv_p x finv_R[:, axis of the tip joint]: linear part of the (constant) LOCAL Jacobian column of the tip joint
   T hook_R[9];  // hook frame on the cube
   T hook_p[3];
 };
@@ -58,7 +59,13 @@ struct DevTable {
   int32_t act_q[kActive];              // q index of each active joint
   int32_t n_passive;
   int32_t passive_q[GIK_MAX_NQ];
+  uint32_t tzero;                      // bit 3*K + c set <=> translation component c of chain joint K is 0 in BOTH arms
 };
+
+// Zero pattern of the Nextage joint translations (NextageaOpen.urdf:580-711): chest (0,0,z) | (x,y,z) | (0,0,z) |
+// (0,y,z) | (x,0,z) | (x,0,0) | (0,0,z).  Kernels are instantiated for "no zeros known" (TZ = 0, any table of the
+// compiled topology) and for this pattern; the launcher picks the specialisation when the table has at least these zeros.
+constexpr uint32_t kNextageTZ = (3u << 0) | (3u << 6) | (1u << 9) | (1u << 13) | (6u << 15) | (3u << 18);
 
 // ------------------------------------------------------------------------------------------------------
 // scalar helpers
@@ -205,15 +212,19 @@ GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
 // frame; A[:, K] receives the LOCAL Jacobian column of chain joint K ([linear; angular]).  On return (B, b)
 // is hand^-1 in the world.  OFF maps chain joint K >= 1 to its slot in the active-joint arrays.
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int K, int OFF>
+template <typename T, int K, int OFF, uint32_t TZ>
 GIK_HD void chain_step(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
                        T (&b)[3], T (&A)[6][7]) {
   constexpr int AX = chain_axis(K), I = (AX + 1) % 3, J = (AX + 2) % 3;
   constexpr int SLOT = K == 0 ? 0 : OFF + K;
   const T ax = B[AX], ay = B[3 + AX], az = B[6 + AX];
-  A[0][K] = b[1] * az - b[2] * ay;
-  A[1][K] = b[2] * ax - b[0] * az;
-  A[2][K] = b[0] * ay - b[1] * ax;
+  if constexpr (K == 6) {  // (B, b) is still the constant frame offset: the column is a table constant
+    A[0][K] = ac.tip_lin[0]; A[1][K] = ac.tip_lin[1]; A[2][K] = ac.tip_lin[2];
+  } else {
+    A[0][K] = b[1] * az - b[2] * ay;
+    A[1][K] = b[2] * ax - b[0] * az;
+    A[2][K] = b[0] * ay - b[1] * ax;
+  }
   A[3][K] = ax; A[4][K] = ay; A[5][K] = az;
   const T c = cs[SLOT], s = sn[SLOT];
 #pragma unroll
@@ -223,19 +234,22 @@ GIK_HD void chain_step(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&
     B[3 * r + J] = s * bi + c * bj;
   }
 #pragma unroll
-  for (int r = 0; r < 3; ++r)    // b <- b - B * t
-    b[r] -= B[3 * r] * ac.t[K][0] + B[3 * r + 1] * ac.t[K][1] + B[3 * r + 2] * ac.t[K][2];
-  if constexpr (K > 0) chain_step<T, K - 1, OFF>(ac, cs, sn, B, b, A);
+  for (int r = 0; r < 3; ++r) {  // b <- b - B * t, one FMA per non-zero translation component
+    if constexpr (!((TZ >> (3 * K + 0)) & 1u)) b[r] -= B[3 * r] * ac.t[K][0];
+    if constexpr (!((TZ >> (3 * K + 1)) & 1u)) b[r] -= B[3 * r + 1] * ac.t[K][1];
+    if constexpr (!((TZ >> (3 * K + 2)) & 1u)) b[r] -= B[3 * r + 2] * ac.t[K][2];
+  }
+  if constexpr (K > 0) chain_step<T, K - 1, OFF, TZ>(ac, cs, sn, B, b, A);
 }
 
-template <typename T, int OFF>
+template <typename T, int OFF, uint32_t TZ>
 GIK_HD void hand_chain(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
                        T (&b)[3], T (&A)[6][7]) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) b[i] = ac.finv_p[i];
-  chain_step<T, 6, OFF>(ac, cs, sn, B, b, A);
+  chain_step<T, 6, OFF, TZ>(ac, cs, sn, B, b, A);
 }
 
 // hook target of one hand: cube * hook offset (tools.getcubeplacement, tools.py:54-59)
@@ -268,11 +282,11 @@ GIK_HD void hand_error(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], T (
 
 // One hand's share of the damped least-squares step.  Returns u = A^T G^-1 e, w = A^T G^-1 c over the six
 // arm joints (G = A A^T + lambda I, A = arm block, c = chest column) and accumulates c.G^-1 e, c.G^-1 c.
-template <typename T, int OFF>
+template <typename T, int OFF, uint32_t TZ>
 GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive],
                       const T (&tgt)[12], T lambda, T (&u)[6], T (&w)[6], T& Sy, T& Sz, T& resid) {
   T B[9], b[3], A[6][7], e[6];
-  hand_chain<T, OFF>(ac, cs, sn, B, b, A);
+  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
   hand_error(B, b, tgt, e);
   resid = sqrt_(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
 
@@ -282,10 +296,10 @@ GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&s
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
-      T g = A[i][1] * A[j][1];
+      T g = (i == j) ? A[i][1] * A[j][1] + lambda : A[i][1] * A[j][1];
 #pragma unroll
       for (int k = 2; k <= 6; ++k) g += A[i][k] * A[j][k];
-      L[i][j] = (i == j) ? g + lambda : g;
+      L[i][j] = g;
     }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -329,15 +343,15 @@ GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&s
 }
 
 // One full iteration at q: residual norms of both hands and the step direction dq = J^+ e.
-template <typename T, bool FAST>
+template <typename T, bool FAST, uint32_t TZ = 0>
 GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T (&tgt)[2][12], T lambda,
                          T (&dq)[kActive], T& residL, T& residR) {
   T cs[kActive], sn[kActive];
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   T uL[6], wL[6], uR[6], wR[6], Sy = T(0), Sz = T(0);
-  hand_pass<T, 0>(tab.arm[0], cs, sn, tgt[0], lambda, uL, wL, Sy, Sz, residL);
-  hand_pass<T, 6>(tab.arm[1], cs, sn, tgt[1], lambda, uR, wR, Sy, Sz, residR);
+  hand_pass<T, 0, TZ>(tab.arm[0], cs, sn, tgt[0], lambda, uL, wL, Sy, Sz, residL);
+  hand_pass<T, 6, TZ>(tab.arm[1], cs, sn, tgt[1], lambda, uR, wR, Sy, Sz, residR);
   const T kappa = div_(Sy, T(1) + Sz);
   dq[0] = kappa;
 #pragma unroll
@@ -361,14 +375,14 @@ GIK_HD void fk_frames(const DevTable<T>& tab, const T (&q)[kActive], T (&frames)
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   T B[9], b[3], A[6][7];
-  hand_chain<T, 0>(tab.arm[0], cs, sn, B, b, A);
+  hand_chain<T, 0, 0>(tab.arm[0], cs, sn, B, b, A);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {  // invert: R = B^T, p = -B^T b
 #pragma unroll
     for (int c = 0; c < 3; ++c) frames[0][3 * r + c] = B[3 * c + r];
     frames[0][9 + r] = -(B[r] * b[0] + B[3 + r] * b[1] + B[6 + r] * b[2]);
   }
-  hand_chain<T, 6>(tab.arm[1], cs, sn, B, b, A);
+  hand_chain<T, 6, 0>(tab.arm[1], cs, sn, B, b, A);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -383,8 +397,8 @@ GIK_HD void frame_jacobians(const DevTable<T>& tab, const T (&q)[kActive], T (&A
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   T B[9], b[3];
-  hand_chain<T, 0>(tab.arm[0], cs, sn, B, b, AL);
-  hand_chain<T, 6>(tab.arm[1], cs, sn, B, b, AR);
+  hand_chain<T, 0, 0>(tab.arm[0], cs, sn, B, b, AL);
+  hand_chain<T, 6, 0>(tab.arm[1], cs, sn, B, b, AR);
 }
 
 }  // namespace gik

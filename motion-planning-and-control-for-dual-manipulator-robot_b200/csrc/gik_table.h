@@ -88,9 +88,25 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
       for (int c = 0; c < 3; ++c) ac.finv_R[3 * r + c] = (T)R[3 * c + r];
       ac.finv_p[r] = (T)(-(R[r] * p[0] + R[3 + r] * p[1] + R[6 + r] * p[2]));
     }
+    {  // constant LOCAL Jacobian column of the tip joint: linear part = finv_p x finv_R[:, axis]
+      const int ax = chain_axis(6);
+      double fi_R[9], fi_p[3];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) fi_R[3 * r + c] = R[3 * c + r];
+        fi_p[r] = -(R[r] * p[0] + R[3 + r] * p[1] + R[6 + r] * p[2]);
+      }
+      const double av[3] = {fi_R[ax], fi_R[3 + ax], fi_R[6 + ax]};
+      ac.tip_lin[0] = (T)(fi_p[1] * av[2] - fi_p[2] * av[1]);
+      ac.tip_lin[1] = (T)(fi_p[2] * av[0] - fi_p[0] * av[2]);
+      ac.tip_lin[2] = (T)(fi_p[0] * av[1] - fi_p[1] * av[0]);
+    }
     for (int i = 0; i < 9; ++i) ac.hook_R[i] = (T)t.hook_R[h][i];
     for (int i = 0; i < 3; ++i) ac.hook_p[i] = (T)t.hook_p[h][i];
   }
+  d.tzero = 0;
+  for (int c = 0; c < 7; ++c)
+    for (int i = 0; i < 3; ++i)
+      if (t.joint_p[chain[0][c]][i] == 0.0 && t.joint_p[chain[1][c]][i] == 0.0) d.tzero |= 1u << (3 * c + i);
   for (int j = 0; j < t.nq; ++j) {
     d.qlo[j] = narrow_lo<T>(t.lower[j]);
     d.qhi[j] = narrow_hi<T>(t.upper[j]);

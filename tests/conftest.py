@@ -85,13 +85,13 @@ class HostSim:
         assert f(ctypes.byref(tc), ctypes.c_int64(n), self._p(q), self._p(J)) == 0
         return J.transpose(3, 0, 1, 2)
 
-    def solve(self, tc, q_rows, pose_rows, dtype, eps=1e-3, dt=1e-2, max_iters=1000, damping=0.0):
+    def solve(self, tc, q_rows, pose_rows, dtype, eps=1e-3, dt=1e-2, max_iters=1000, damping=0.0, flags=0):
         from gik_b200._cabi import GikParams
         q0 = np.ascontiguousarray(np.asarray(q_rows, dtype).T)
         pose = np.ascontiguousarray(np.asarray(pose_rows, dtype).T)
         nq, n = q0.shape
         q = np.zeros((nq, n), dtype); c = np.zeros(n, np.uint8); it = np.zeros(n, np.int32); r = np.zeros((2, n), dtype)
-        prm = GikParams(eps, dt, damping, max_iters, 0)
+        prm = GikParams(eps, dt, damping, max_iters, flags)
         f = self.lib.hostsim_solve_f32 if dtype == np.float32 else self.lib.hostsim_solve_f64
         assert f(ctypes.byref(tc), ctypes.c_int64(n), self._p(q0), self._p(pose), ctypes.byref(prm), self._p(q),
                  self._p(c), self._p(it), self._p(r)) == 0

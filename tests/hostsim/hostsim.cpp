@@ -53,6 +53,7 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
   int rc = build_dev_table<T>(*tab, d);
   if (rc) return rc;
   const T eps = (T)prm->eps, dt = (T)prm->dt, lambda = (T)prm->damping;
+  const bool generic = (prm->flags & 1) != 0;   // test hook: force the TZ = 0 instantiation
   for (int64_t i = 0; i < n; ++i) {
     T q[kActive], cube[12], tgt[2][12], dq[kActive], rL = 0, rR = 0;
     for (int a = 0; a < kActive; ++a) q[a] = q_init[(int64_t)d.act_q[a] * n + i];
@@ -62,7 +63,9 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
     int it = 0;
     bool ok = false;
     for (;;) {
-      ik_iteration<T, true>(d, q, tgt, lambda, dq, rL, rR);
+      // same specialisation rule as launch_solve() in csrc/gik_kernels.cu
+      if ((d.tzero & kNextageTZ) == kNextageTZ && !generic) ik_iteration<T, true, kNextageTZ>(d, q, tgt, lambda, dq, rL, rR);
+      else ik_iteration<T, true, 0>(d, q, tgt, lambda, dq, rL, rR);
       ok = (rL < eps) && (rR < eps) && (it < prm->max_iters);
       if (ok || it >= prm->max_iters) break;
       apply_step(d, q, dq, dt);

@@ -47,3 +47,12 @@ def test_hostsim_damping_shortens_step(table_c, hostsim):
     q0, *_ = hostsim.solve(table_c, np.zeros((4, 15)), P, np.float64, max_iters=1)
     q1, *_ = hostsim.solve(table_c, np.zeros((4, 15)), P, np.float64, max_iters=1, damping=1.0)
     assert (np.abs(q1).sum(1) < np.abs(q0).sum(1)).all()
+
+
+def test_hostsim_translation_sparsity_specialisation_is_exact(table_c, hostsim):
+    # the Nextage-pattern instantiation only drops FMAs whose translation operand is exactly 0: same bits
+    P = make_poses(16, 9)
+    for dt in (np.float64, np.float32):
+        a = hostsim.solve(table_c, np.zeros((16, 15)), P, dt, max_iters=50)
+        b = hostsim.solve(table_c, np.zeros((16, 15)), P, dt, max_iters=50, flags=1)     # generic instantiation
+        assert np.abs(a[0] - b[0]).max() < (1e-13 if dt == np.float64 else 1e-5)
