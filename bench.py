@@ -36,12 +36,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"], help="default: f32 (f64 for --config 3)")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="problems per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 (default, the metric's workload), 3 restarts fp64, 4 edge projection, 5 sharded sweep")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the result all-gather")
+    args = ap.parse_args()
+    if args.dtype is None:
+        args.dtype = "f64" if args.config == 3 else "f32"
+    return args
 
 
 def workload_name(n, dtype):
@@ -165,6 +171,129 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def workspace_positions(torch, n, dev, dtype, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lo = torch.tensor(WORKSPACE_LO, device=dev, dtype=dtype)
+    hi = torch.tensor(WORKSPACE_HI, device=dev, dtype=dtype)
+    return lo + torch.rand((n, 3), device=dev, dtype=dtype, generator=g) * (hi - lo)
+
+
+def pose_rows_from(torch, pos):
+    n = pos.shape[0]
+    return torch.cat([torch.eye(3, device=pos.device, dtype=pos.dtype).reshape(1, 9).expand(n, 9), pos], 1).contiguous()
+
+
+class Workload:
+    """One BASELINE config on one rank: `launch()` enqueues the kernels of one step on the current stream and
+    returns the tensors a gather would ship; `solves` = problems solved per step on this rank; `iterations()` = descent
+    iterations executed by the last step (device scalar); `converged()` = fraction converged."""
+    name = ""
+    solves = 0
+    kernel = "gik_solve_kernel"
+
+
+class Config2(Workload):
+    def __init__(self, torch, solver, n, rank, dtype, seed_base=1000):
+        dev = solver.device
+        self.torch, self.solver, self.solves = torch, solver, n
+        self.pose_rows = pose_rows_from(torch, workspace_positions(torch, n, dev, dtype, seed_base + rank))
+        self.pose = self.pose_rows.t().contiguous()                 # SoA [12][n]
+        self.q0 = torch.zeros((15, n), device=dev, dtype=dtype)     # SoA [15][n]
+        self.out = (torch.empty_like(self.q0), torch.empty(n, dtype=torch.uint8, device=dev),
+                    torch.empty(n, dtype=torch.int32, device=dev), torch.empty((2, n), dtype=dtype, device=dev))
+        self.name = workload_name(n, "fp32" if dtype == torch.float32 else "fp64")
+
+    def launch(self):
+        q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out)
+        return q, conv
+
+    def iterations(self):
+        return self.out[2].sum(dtype=self.torch.int64).double()
+
+    def converged(self):
+        return self.out[1].double().mean()
+
+
+class Config3(Workload):
+    """65,536 placements x 64 random-restart initial q (restart 0 = zeros), best-of, fp64."""
+    DAMPING = 1e-6
+
+    def __init__(self, torch, solver, n_place, restarts, rank, dtype):
+        dev = solver.device
+        self.torch, self.solver, self.n_place, self.R = torch, solver, n_place, restarts
+        self.solves = n_place * restarts
+        pos = workspace_positions(torch, n_place, dev, dtype, 1 + 7919 * rank)
+        rows = pose_rows_from(torch, pos)
+        self.pose = rows.unsqueeze(1).expand(n_place, restarts, 12).reshape(-1, 12).t().contiguous()
+        lo, hi = solver.limits(dtype)
+        g = torch.Generator(device=dev).manual_seed(2 + 7919 * rank)
+        cand = lo + torch.rand((n_place, restarts, 15), device=dev, dtype=dtype, generator=g) * (hi - lo)
+        cand[:, 0, :] = 0
+        self.q0 = cand.reshape(-1, 15).t().contiguous()
+        n = self.solves
+        self.out = (torch.empty_like(self.q0), torch.empty(n, dtype=torch.uint8, device=dev),
+                    torch.empty(n, dtype=torch.int32, device=dev), torch.empty((2, n), dtype=dtype, device=dev))
+        self.best = None
+        self.name = (f"config3: {n_place} workspace placements x {restarts} restarts (restart 0 = q0, others uniform in the "
+                     f"joint limits), best-of, {'fp64' if dtype == torch.float64 else 'fp32'}, damping {self.DAMPING}")
+
+    def launch(self):
+        q, conv, _, resid = self.solver.solve_soa(self.q0, self.pose, out=self.out, damping=self.DAMPING)
+        self.best = self.solver.best_of_soa(q, conv, resid, self.n_place, self.R)
+        return self.best[0], self.best[1]
+
+    def iterations(self):
+        return self.out[2].sum(dtype=self.torch.int64).double()
+
+    def converged(self):
+        return self.out[1].double().mean()
+
+    def extra(self):
+        return {"placements_with_a_converged_restart": float(self.best[1].double().mean()),
+                "restart0_converged": float(self.out[1].reshape(self.n_place, self.R)[:, 0].double().mean())}
+
+
+class Config4(Workload):
+    """path.py edge projection: E edges x S interpolated placements, warm-started along each edge, march stops at the
+    first non-converged step.  Step 0 starts from a converged q at cube_a."""
+
+    def __init__(self, torch, solver, n_edges, steps, rank, dtype):
+        dev = solver.device
+        self.torch, self.solver, self.E, self.S = torch, solver, n_edges, steps
+        # endpoints a: workspace placements whose IK from q0 converges (oversample, keep the first E)
+        cand = pose_rows_from(torch, workspace_positions(torch, 3 * n_edges, dev, dtype, 3 + 7919 * rank))
+        q, conv = solver.solve(torch.zeros(15, device=dev, dtype=dtype), cand, dtype=dtype)
+        keep = torch.nonzero(conv).flatten()[:n_edges]
+        assert keep.numel() == n_edges, "not enough reachable edge starts"
+        self.q_start = q[keep].t().contiguous()
+        self.pose_a = cand[keep].t().contiguous()
+        self.pose_b = pose_rows_from(torch, workspace_positions(torch, n_edges, dev, dtype, 4 + 7919 * rank)).t().contiguous()
+        self.ns = torch.full((n_edges,), steps, dtype=torch.int32, device=dev)
+        self.res = None
+        self.solves = n_edges * steps          # upper bound; the executed count is reported from n_valid
+        self.name = (f"config4: {n_edges} cube-pose edges x {steps} interpolated placements (SE3.Interpolate), IK "
+                     f"warm-started along each edge, stop at first failure, {'fp32' if dtype == torch.float32 else 'fp64'}")
+
+    def launch(self):
+        self.res = self.solver.project_edges_soa(self.q_start, self.pose_a, self.pose_b, self.ns, self.S)
+        return self.res[0], self.res[1]
+
+    def executed(self):
+        nv = self.res[1]
+        return (nv + (nv < self.S).to(nv.dtype)).sum(dtype=self.torch.int64).double()   # + the failing solve
+
+    def iterations(self):
+        return self.res[2].sum(dtype=self.torch.int64).double()
+
+    def converged(self):
+        return self.res[1].double().sum() / self.executed()
+
+    def extra(self):
+        nv = self.res[1].double()
+        return {"edges_fully_projected": float((nv == self.S).double().mean()), "mean_valid_steps": float(nv.mean()),
+                "solves_executed": float(self.executed())}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -182,32 +311,39 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     esz = 4 if args.dtype == "f32" else 8
-    n = args.n
-    n_total = n * world
-
     solver = gik_b200.GraspIK(gik_b200.nextage_table(), dev)
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    lo = torch.tensor(WORKSPACE_LO, device=dev, dtype=dtype)
-    hi = torch.tensor(WORKSPACE_HI, device=dev, dtype=dtype)
-    pos = lo + torch.rand((n, 3), device=dev, dtype=dtype, generator=g) * (hi - lo)
-    pose_rows = torch.cat([torch.eye(3, device=dev, dtype=dtype).reshape(1, 9).expand(n, 9), pos], 1).contiguous()
-    pose = pose_rows.t().contiguous()                       # SoA [12][n]
-    q0 = torch.zeros((15, n), device=dev, dtype=dtype)      # SoA [15][n]
-    out = (torch.empty_like(q0), torch.empty(n, dtype=torch.uint8, device=dev),
-           torch.empty(n, dtype=torch.int32, device=dev), torch.empty((2, n), dtype=dtype, device=dev))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step():
-        flush.fill_(1)                                       # L2 flush between iterations
-        q, conv, iters, resid = solver.solve_soa(q0, pose, out=out)
-        if world > 1:
-            return gdist.all_gather_results(q, conv, n_total)
-        return q, conv
+    scaling = "weak"
+    if args.config == 2:
+        wl = Config2(torch, solver, args.n, rank, dtype)
+    elif args.config == 3:
+        wl = Config3(torch, solver, args.n if args.n != N_PER_GPU else 65536, 64, rank, dtype)
+    elif args.config == 4:
+        wl = Config4(torch, solver, args.n if args.n != N_PER_GPU else 4096, 256, rank, dtype)
+    else:   # config 5: 64 Mi config-2 problems sharded over the ranks (strong scaling) + all-gather
+        total = args.n if args.n != N_PER_GPU else 64 << 20
+        lo_i, hi_i = gdist.shard_bounds(total, rank, world)
+        wl = Config2(torch, solver, hi_i - lo_i, rank, dtype, seed_base=4000)
+        wl.name = f"config5: {total} config-2 problems sharded over {world} GPU(s) + all-gather of q/converged; " + wl.name
+        scaling = "strong"
+    gather = world > 1 and not args.no_gather
+    n_total_gather = wl.solves * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def step(ev=None):
+        flush.fill_(1)                                       # L2 flush between iterations
+        if ev:
+            ev[0].record()
+        q, conv = wl.launch()
+        if ev:
+            ev[1].record()
+        if gather and args.config in (2, 5):
+            gdist.all_gather_results(q, conv, n_total_gather)
 
     for _ in range(max(args.warmup, 0)):
         step()
@@ -224,12 +360,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        flush.fill_(1)
-        kev[k][0].record()
-        q, conv, iters, resid = solver.solve_soa(q0, pose, out=out)
-        kev[k][1].record()
-        if world > 1:
-            gdist.all_gather_results(q, conv, n_total)
+        step(kev[k])
     e1.record()
     barrier()
     if sampler:
@@ -243,19 +374,19 @@ def run_b200(args):
     ms_total, kernel_ms = t.tolist()
     ms_per_step = ms_total / max(args.steps, 1)
 
-    conv_frac = out[1].float().mean()
-    iters_sum = out[2].sum(dtype=torch.int64)
-    stats = torch.stack([conv_frac.double(), iters_sum.double()])
+    solves_step = wl.executed() if hasattr(wl, "executed") else torch.tensor(float(wl.solves), device=dev, dtype=torch.float64)
+    stats = torch.stack([wl.converged() * solves_step, wl.iterations(), solves_step])
     if world > 1:
         dist.all_reduce(stats)
-        stats[0] /= world
-    conv_frac, iters_sum = stats.tolist()
+    conv_solves, iters_sum, solves_all = stats.tolist()          # per step, all ranks
+    conv_frac = conv_solves / solves_all
 
-    # ---- e2e: public batched API with pinned HOST buffers, copies inside the timed region
+    # ---- e2e: public batched API with pinned HOST buffers, copies inside the timed region (default workload only)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.config == 2:
+        n = wl.solves
         q_host = torch.zeros((n, 15), dtype=dtype).pin_memory()
-        pose_host = pose_rows.cpu().pin_memory()
+        pose_host = wl.pose_rows.cpu().pin_memory()
         q_res = torch.empty((n, 15), dtype=dtype).pin_memory()
         c_res = torch.empty((n,), dtype=torch.bool).pin_memory()
 
@@ -282,10 +413,11 @@ def run_b200(args):
         te = torch.tensor([max(a0.elapsed_time(a1), wall)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_total * args.steps / (te.item() * 1e-3), "unit": "solves/s",
+        e2e = {"value": n * world * args.steps / (te.item() * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(n * (15 + 12) * esz), "d2h_bytes_per_step": int(n * (15 * esz + 1)),
                "api": "computeqgrasppose_batch (pinned host row-major in/out)"}
 
+    extra = wl.extra() if hasattr(wl, "extra") else {}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -296,16 +428,15 @@ def run_b200(args):
     peak = gik_b200.fma_peak_tflops(local, esz)
     iters_per_launch = iters_sum / world
     achieved = iters_per_launch * fpi / (kernel_ms * 1e-3) * 1e-12
-    bytes_algo = gik_b200.bytes_per_solve(esz) * n
-    import json as _json
+    bytes_algo = gik_b200.bytes_per_solve(esz) * solves_all / world
     hbm_peak = None
     try:
-        hbm_peak = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
     traffic = None
     try:
-        traffic = _json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.dtype)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.dtype) if args.config == 2 else None
     except Exception:
         pass
     roofline = {
@@ -321,7 +452,7 @@ def run_b200(args):
     }
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.config == 2:
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or 256 * cores
         rate, threads, secs = cpu_solve_rate(n_sample)
@@ -329,15 +460,17 @@ def run_b200(args):
                "sample": f"{n_sample} problems of the same workload ({secs:.1f} s), C oracle (Jacobi-SVD pinv, -O3 "
                          f"-march=native, OpenMP {threads} threads); the Python+pinocchio reference cannot be installed here"}
 
+    cfg = {"workload": wl.name, "problems_per_gpu_per_step": solves_all / world,
+           "l2": "256 MB flush write before every step (inside the timed region)",
+           "collective": ("all_gather of q [15][n] + converged [n] per step" if gather and args.config in (2, 5) else "none"),
+           "converged_fraction": conv_frac, "mean_iterations": iters_sum / solves_all}
+    cfg.update(extra)
     line = {
-        "metric": METRIC, "value": n_total * args.steps / (ms_total * 1e-3), "unit": "solves/s", "n_gpus": world,
+        "metric": METRIC, "value": solves_all * args.steps / (ms_total * 1e-3), "unit": "solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload_name(n, "fp32" if esz == 4 else "fp64"), "problems_per_gpu": n,
-                   "l2": "256 MB flush write before every step (inside the timed region)",
-                   "collective": "all_gather of q [15][n] + converged [n] per step" if world > 1 else "none",
-                   "converged_fraction": conv_frac, "mean_iterations": iters_sum / n_total},
-        "converged_solves_per_s": conv_frac * n_total * args.steps / (ms_total * 1e-3),
+        "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": cfg,
+        "converged_solves_per_s": conv_solves * args.steps / (ms_total * 1e-3),
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
