@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <new>
 
 #include "gik_table.h"
@@ -52,6 +53,7 @@ struct SolveArgs {
   T eps, dt, lambda;
   int32_t max_iters;
   int32_t lanes;        // problems per warp kept in flight (1..32); < 32 spreads a small batch over more SMs
+  unsigned long long* queue;  // work queue head (zeroed on the stream before the launch): next problem to hand out
 };
 
 template <typename T>
@@ -64,8 +66,6 @@ template <typename T, int MODE, uint32_t TZ>
 __global__ void __launch_bounds__(GIK_THREADS, Launch<T>::kMinBlocks)
 gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n = a.n;
   const int L = a.lanes;
   const bool enabled = lane < L;
@@ -78,21 +78,28 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
 #pragma unroll
     for (int c = 0; c < 12; ++c) tgt[h][c] = (c % 4 == 0 && c < 9) ? T(1) : T(0);
 
-  int64_t seq = 0;      // problems handed out to this warp so far (warp-uniform)
   int64_t idx = -1;     // problem (or edge) this lane works on
   bool active = false;
+  bool exhausted = false;   // warp-uniform: the queue has handed out every problem
   int it = 0;
   // edge mode state
   int step = 0, nsteps = 0, it_total = 0;
 
   for (;;) {
-    // ---------------- refill: lanes without work pull the next problem of this warp ----------------
-    const unsigned need = __ballot_sync(0xffffffffu, enabled && !active);
+    // ---------------- refill: lanes without work pull the next problems from the global queue ----------------
+    // One atomicAdd per warp per refill (leader lane, count = lanes in need), so problems are handed out in index
+    // order to whichever lane frees up first: the tail of the launch is bounded by ONE problem's duration instead
+    // of by the slowest statically assigned lane.  The first refill of a warp takes 32 consecutive problems
+    // (coalesced loads).  A problem's arithmetic does not depend on the lane it lands on: results are bit-identical.
+    const unsigned need = exhausted ? 0u : __ballot_sync(0xffffffffu, enabled && !active);
     if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
       if (enabled && !active) {
-        const int64_t s = seq + __popc(need & ((1u << lane) - 1u));
-        const int64_t chunk = s / L;
-        const int64_t cand = (chunk * n_warps + warp) * L + (s - chunk * L);
+        const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
         if (cand < n) {
           idx = cand;
           active = true;
@@ -121,9 +128,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           hook_target(tab.arm[1], cube, tgt[1]);
         }
       }
-      seq += __popc(need);
-      if (!__any_sync(0xffffffffu, active)) break;
     }
+    if (exhausted && !__any_sync(0xffffffffu, active)) break;
 
     // ---------------- one descent iteration for every lane ----------------
     T dq[kActive], rL, rR;
@@ -288,7 +294,10 @@ struct gik_handle_s {
   gik_table_t host;
   DevTable<float> tab32;
   DevTable<double> tab64;
+  unsigned long long* queues;        // device: kQueueSlots work-queue heads, one per launch in flight
+  std::atomic<uint32_t> next_queue;
 };
+static constexpr uint32_t kQueueSlots = 1024;   // launches that may be in flight on one handle at once
 static constexpr uint32_t kMagic = 0x67696b31u;  // "gik1"
 
 namespace {
@@ -358,6 +367,9 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   int rc = solve_dims<T, MODE>(h, a.n, &blocks, &lanes);
   if (rc) return rc;
   a.lanes = lanes;
+  a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
+  cudaError_t qe = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+  if (qe != cudaSuccess) return (int)qe;
   const DevTable<T>& tab = table_of<T>(h);
   if ((tab.tzero & kNextageTZ) == kNextageTZ)   // table has (at least) the Nextage zero pattern: skip those FMAs
     gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, (cudaStream_t)stream>>>(tab, a);
@@ -483,6 +495,12 @@ int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out) {
   e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) { delete h; return (int)e; }
   h->device = device;
+  {
+    DeviceGuard g(device);
+    if (g.err == cudaSuccess) g.err = cudaMalloc(&h->queues, kQueueSlots * sizeof(unsigned long long));
+    if (g.err != cudaSuccess) { delete h; return (int)g.err; }
+  }
+  h->next_queue.store(0);
   h->magic = kMagic;
   *out = h;
   return GIK_OK;
@@ -491,6 +509,10 @@ int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out) {
 int gik_destroy(gik_handle_t h) {
   if (bad_handle(h)) return GIK_E_HANDLE;
   h->magic = 0;
+  {
+    DeviceGuard g(h->device);
+    cudaFree(h->queues);
+  }
   delete h;
   return GIK_OK;
 }
