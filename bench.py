@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 (default, the metric's workload), 3 restarts fp64, 4 edge projection, 5 sharded sweep")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the result all-gather")
+    ap.add_argument("--kernel", default=None, choices=["lane", "pair"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = "f64" if args.config == 3 else "f32"
@@ -189,7 +190,7 @@ class Workload:
     iterations executed by the last step (device scalar); `converged()` = fraction converged."""
     name = ""
     solves = 0
-    kernel = "gik_solve_kernel"
+    kernel_choice = None
 
 
 class Config2(Workload):
@@ -204,7 +205,7 @@ class Config2(Workload):
         self.name = workload_name(n, "fp32" if dtype == torch.float32 else "fp64")
 
     def launch(self):
-        q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out)
+        q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out, kernel=self.kernel_choice)
         return q, conv
 
     def iterations(self):
@@ -238,7 +239,7 @@ class Config3(Workload):
                      f"joint limits), best-of, {'fp64' if dtype == torch.float64 else 'fp32'}, damping {self.DAMPING}")
 
     def launch(self):
-        q, conv, _, resid = self.solver.solve_soa(self.q0, self.pose, out=self.out, damping=self.DAMPING)
+        q, conv, _, resid = self.solver.solve_soa(self.q0, self.pose, out=self.out, damping=self.DAMPING, kernel=self.kernel_choice)
         self.best = self.solver.best_of_soa(q, conv, resid, self.n_place, self.R)
         return self.best[0], self.best[1]
 
@@ -275,7 +276,7 @@ class Config4(Workload):
                      f"warm-started along each edge, stop at first failure, {'fp32' if dtype == torch.float32 else 'fp64'}")
 
     def launch(self):
-        self.res = self.solver.project_edges_soa(self.q_start, self.pose_a, self.pose_b, self.ns, self.S)
+        self.res = self.solver.project_edges_soa(self.q_start, self.pose_a, self.pose_b, self.ns, self.S, kernel=self.kernel_choice)
         return self.res[0], self.res[1]
 
     def executed(self):
@@ -326,6 +327,7 @@ def run_b200(args):
         wl = Config2(torch, solver, hi_i - lo_i, rank, dtype, seed_base=4000)
         wl.name = f"config5: {total} config-2 problems sharded over {world} GPU(s) + all-gather of q/converged; " + wl.name
         scaling = "strong"
+    wl.kernel_choice = args.kernel
     gather = world > 1 and not args.no_gather
     n_total_gather = wl.solves * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2

@@ -70,8 +70,14 @@ typedef struct gik_params_s {
   double  dt;         /* step length: q <- clamp(q + dt * J^+ e) */
   double  damping;    /* lambda in J^T (J J^T + lambda I)^-1 e; 0 = pseudo-inverse */
   int32_t max_iters;  /* iteration cap */
-  int32_t flags;      /* reserved, must be 0 */
+  int32_t flags;      /* 0, or one GIK_F_* scheduling override (results are unaffected) */
 } gik_params_t;
+
+/* gik_params_t.flags: by default the launcher picks the kernel mapping from the batch size -- one problem per lane
+ * when the batch can occupy at least half of the lanes of every resident warp, one problem per lane PAIR (one hand
+ * per lane) below that.  These force one mapping (A/B measurements, tests). */
+#define GIK_F_LANE_KERNEL 2
+#define GIK_F_PAIR_KERNEL 4
 
 typedef struct gik_handle_s* gik_handle_t;
 

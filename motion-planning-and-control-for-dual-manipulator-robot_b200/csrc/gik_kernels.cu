@@ -50,7 +50,7 @@ struct SolveArgs {
   int32_t max_steps;
   // common
   int64_t n;
-  T eps, dt, lambda;
+  T eps2, dt, lambda;   // eps2 = eps^2: the predicate compares squared norms
   int32_t max_iters;
   int32_t lanes;        // problems per warp kept in flight (1..32); < 32 spreads a small batch over more SMs
   unsigned long long* queue;  // work queue head (zeroed on the stream before the launch): next problem to hand out
@@ -134,7 +134,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     // ---------------- one descent iteration for every lane ----------------
     T dq[kActive], rL, rR;
     ik_iteration<T, true, TZ>(tab, q, tgt, a.lambda, dq, rL, rR);
-    const bool ok = (rL < a.eps) && (rR < a.eps) && (it < a.max_iters);
+    const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
     const bool done = ok || (it >= a.max_iters);
 
     if (!done) {
@@ -153,7 +153,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         }
         a.conv[idx] = ok ? 1 : 0;
         if (a.iters) a.iters[idx] = it;
-        if (a.resid) { a.resid[idx] = rL; a.resid[n + idx] = rR; }
+        if (a.resid) { a.resid[idx] = sqrt_(rL); a.resid[n + idx] = sqrt_(rR); }
         active = false;
       } else {
         it_total += it;
@@ -184,6 +184,144 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           if (a.iters) a.iters[idx] = it_total;
           active = false;
         }
+      }
+    }
+  }
+}
+
+
+// ========================================================================================================
+// Pair kernel: ONE PROBLEM PER LANE PAIR (even lane = left hand, odd lane = right hand).  Each lane walks its
+// own hand's chain, factors its own 6x6 block and solves its two right-hand sides; the pair meets in three
+// warp shuffles per iteration (the two Sherman-Morrison scalars and the residual).  Per-warp instruction count per
+// iteration is about half of the lane kernel's, so this is the kernel for batches too small to give every lane of
+// the machine its own problem (path.py edge projection: 4096 chains; the single-solve drop-in) -- there the cost
+// is issue slots per chain-iteration, not lane occupancy.  Same operations on the same values as the lane kernel.
+// Arm constants are lane dependent: they come from the kernel-parameter table by indexed constant loads.
+// ========================================================================================================
+#ifndef GIK_MINB_PAIR_F32
+#define GIK_MINB_PAIR_F32 5
+#endif
+#ifndef GIK_MINB_PAIR_F64
+#define GIK_MINB_PAIR_F64 4   // 128 registers + L1 spills: measured best (7.07M vs 6.91M at 3, 6.26M at 2 blocks/SM)
+#endif
+template <typename T> struct LaunchPair;
+template <> struct LaunchPair<float>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
+template <> struct LaunchPair<double> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64; };
+
+template <typename T, int MODE, uint32_t TZ>
+__global__ void __launch_bounds__(GIK_THREADS, LaunchPair<T>::kMinBlocks)
+gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
+  const int lane = threadIdx.x & 31;
+  const int h = lane & 1;                       // hand of this lane
+  const int off = 1 + 6 * h;                    // first active-joint slot of this hand's arm
+  const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
+  const int64_t n = a.n;
+  const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
+  const ArmConst<T>& ac = tab.arm[h];
+
+  T q[7], tgt[12];                              // q[0] = chest (kept by both lanes), q[1..6] = this hand's arm
+#pragma unroll
+  for (int i = 0; i < 7; ++i) q[i] = T(0);
+#pragma unroll
+  for (int c = 0; c < 12; ++c) tgt[c] = (c % 4 == 0 && c < 9) ? T(1) : T(0);
+
+  int64_t idx = -1;
+  bool active = false, exhausted = false;
+  int it = 0, step = 0, nsteps = 0, it_total = 0;
+
+  for (;;) {
+    const unsigned need = exhausted ? 0u : (__ballot_sync(0xffffffffu, enabled && !active) & 0x55555555u);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
+      if (enabled && !active) {
+        const int64_t cand = (int64_t)base + __popc(need & lower_pairs);
+        if (cand < n) {
+          idx = cand;
+          active = true;
+          it = 0;
+          q[0] = __ldg(a.q_init + (int64_t)tab.act_q[0] * n + idx);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) q[1 + k] = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * n + idx);
+          T cube[12];
+          load_cube(a.pose, n, idx, cube);
+          if (MODE == MODE_EDGES) {
+            nsteps = __ldg(a.num_steps + idx);
+            step = 1;
+            it_total = 0;
+            T cb[12], xi[6], ca[12];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) ca[c] = cube[c];
+            load_cube(a.pose_b, n, idx, cb);
+            se3_delta(ca, cb, xi);
+            se3_advance(ca, xi, T(1) / T(nsteps), cube);
+            if (nsteps < 1) {
+              if (h == 0) { a.n_valid[idx] = 0; if (a.iters) a.iters[idx] = 0; }
+              active = false;
+            }
+          }
+          hook_target(ac, cube, tgt);
+        }
+      }
+    }
+    if (exhausted && !__any_sync(0xffffffffu, active)) break;
+
+    // ---------------- one descent iteration: this lane's hand ----------------
+    T cs[kActive], sn[kActive], u[6], w[6], Sy, Sz, r;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
+    hand_pass<T, 0, TZ>(ac, cs, sn, tgt, a.lambda, u, w, Sy, Sz, r);
+    const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
+    const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
+    const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
+    const T rL = h ? r_o : r, rR = h ? r : r_o;
+    const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
+    const bool done = ok || (it >= a.max_iters);
+
+    if (!done) {
+      q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * (u[k] - kappa * w[k])), tab.hi[off + k]);
+      ++it;
+    } else if (active) {
+      const bool batch = (MODE == MODE_BATCH);
+      if (!batch) it_total += it;
+      if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
+        T* dst = batch ? a.q_out : a.q_out + (int64_t)(step - 1) * tab.nq * n;
+        const bool moved = batch ? (it > 0) : (it_total > 0);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * n + idx] = q[1 + k];
+        if (h == 0) {
+          dst[(int64_t)tab.act_q[0] * n + idx] = q[0];
+          for (int p = 0; p < tab.n_passive; ++p) {
+            const int j = tab.passive_q[p];
+            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
+            dst[(int64_t)j * n + idx] = v;
+          }
+        }
+      }
+      if (batch) {
+        if (h == 0) { a.conv[idx] = ok ? 1 : 0; if (a.iters) a.iters[idx] = it; }
+        if (a.resid) a.resid[(int64_t)h * n + idx] = sqrt_(r);
+        active = false;
+      } else if (ok && step < nsteps) {
+        ++step;
+        it = 0;
+        T ca[12], cb[12], xi[6], cube[12];
+        load_cube(a.pose, n, idx, ca);
+        load_cube(a.pose_b, n, idx, cb);
+        se3_delta(ca, cb, xi);
+        se3_advance(ca, xi, T(step) / T(nsteps), cube);
+        hook_target(ac, cube, tgt);
+      } else {
+        if (h == 0) { a.n_valid[idx] = ok ? step : step - 1; if (a.iters) a.iters[idx] = it_total; }
+        active = false;
       }
     }
   }
@@ -319,7 +457,9 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
-  if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 || p->flags != 0)
+  if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) != 0 ||
+      (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
 }
@@ -328,53 +468,77 @@ template <typename T> const DevTable<T>& table_of(gik_handle_t h);
 template <> const DevTable<float>& table_of<float>(gik_handle_t h) { return h->tab32; }
 template <> const DevTable<double>& table_of<double>(gik_handle_t h) { return h->tab64; }
 
-// Grid for the persistent solver: resident blocks per SM x SM count, shrunk for small batches; `lanes` < 32
-// spreads a batch that cannot fill the machine over more warps (one warp instruction costs the same issue
-// slot whether 1 or 32 lanes are live, so idle SM sub-partitions are the more expensive waste).
-template <typename T, int MODE>
-int solve_dims(gik_handle_t h, int64_t n, int* blocks, int* lanes) {
+// Grid for the persistent solvers: resident blocks per SM x SM count, shrunk for small batches.  `per_warp` = problems
+// a warp keeps in flight (lane kernel: up to 32 lanes; pair kernel: up to 16 lane pairs); a value below the maximum
+// spreads a batch that cannot fill the machine over more warps (one warp instruction costs the same issue slot whether
+// 1 or 32 lanes are live, so idle SM sub-partitions are the more expensive waste).
+template <typename Kernel>
+int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* blocks, int* per_warp, int64_t* max_warps_out) {
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gik_solve_kernel<T, MODE, 0>, GIK_THREADS, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, GIK_THREADS, 0);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
   const int64_t warps_per_block = GIK_THREADS / 32;
   const int64_t max_blocks = (int64_t)h->sm_count * occ;
   const int64_t max_warps = max_blocks * warps_per_block;
-  int L = 32;
-  if (n < max_warps * 32) {
+  int L = max_per_warp;
+  if (n < max_warps * max_per_warp) {
     L = (int)((n + max_warps - 1) / max_warps);
     if (L < 1) L = 1;
-    if (L > 32) L = 32;
+    if (L > max_per_warp) L = max_per_warp;
   }
   int64_t warps = (n + L - 1) / L;
   int64_t b = (warps + warps_per_block - 1) / warps_per_block;
   if (b > max_blocks) b = max_blocks;
   if (b < 1) b = 1;
   *blocks = (int)b;
-  *lanes = L;
+  *per_warp = L;
+  if (max_warps_out) *max_warps_out = max_warps;
   return GIK_OK;
+}
+
+// fp32: lane kernel when the batch can give (at least) half of the lanes of every resident warp a problem, pair kernel
+// below that.  fp64: always the pair kernel -- one hand per lane halves the live state, which at 2 registers per value
+// is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
+// params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
+template <typename T, int MODE>
+int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair) {
+  int64_t max_warps = 0;
+  int rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+  if (rc) return rc;
+  *pair = sizeof(T) == 8 || n <= 16 * max_warps;
+  if (flags & GIK_F_LANE_KERNEL) *pair = false;
+  if (flags & GIK_F_PAIR_KERNEL) *pair = true;
+  if (*pair) rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
+  return rc;
 }
 
 template <typename T, int MODE>
 int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void* stream) {
-  a.eps = (T)prm->eps;
+  a.eps2 = (T)(prm->eps * prm->eps);
   a.dt = (T)prm->dt;
   a.lambda = (T)prm->damping;
   a.max_iters = prm->max_iters;
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int blocks = 0, lanes = 32;
-  int rc = solve_dims<T, MODE>(h, a.n, &blocks, &lanes);
+  bool pair = false;
+  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair);
   if (rc) return rc;
   a.lanes = lanes;
   a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
   cudaError_t qe = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), (cudaStream_t)stream);
   if (qe != cudaSuccess) return (int)qe;
   const DevTable<T>& tab = table_of<T>(h);
-  if ((tab.tzero & kNextageTZ) == kNextageTZ)   // table has (at least) the Nextage zero pattern: skip those FMAs
-    gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, (cudaStream_t)stream>>>(tab, a);
-  else
-    gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, (cudaStream_t)stream>>>(tab, a);
+  const bool nx = (tab.tzero & kNextageTZ) == kNextageTZ;   // table has (at least) the Nextage zero pattern: skip those FMAs
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pair) {
+    if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+  } else {
+    if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    else gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -573,8 +737,9 @@ int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blo
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int b = 0, l = 32, rc;
-  if (elem_size == 4) rc = solve_dims<float, MODE_BATCH>(h, n, &b, &l);
-  else if (elem_size == 8) rc = solve_dims<double, MODE_BATCH>(h, n, &b, &l);
+  bool pair = false;
+  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, 0, &b, &l, &pair);
+  else if (elem_size == 8) rc = choose_launch<double, MODE_BATCH>(h, n, 0, &b, &l, &pair);
   else return GIK_E_PARAM;
   if (rc) return rc;
   *blocks = b; *threads = GIK_THREADS;

@@ -93,8 +93,12 @@ class GraspIK:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _params(self, eps, dt, max_iters, damping) -> _cabi.GikParams:
-        return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), 0)
+    _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4}     # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL
+
+    def _params(self, eps, dt, max_iters, damping, kernel=None) -> _cabi.GikParams:
+        if kernel not in self._KERNEL_FLAGS:
+            raise ValueError(f"kernel must be one of {list(self._KERNEL_FLAGS)}")
+        return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), self._KERNEL_FLAGS[kernel])
 
     def _chk_dev(self, *ts):
         for t in ts:
@@ -131,9 +135,10 @@ class GraspIK:
         return out
 
     def solve_soa(self, q_init: torch.Tensor, pose: torch.Tensor, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
-                  damping=0.0, out=None):
+                  damping=0.0, out=None, kernel=None):
         """q_init [nq][n], pose [12][n] (contiguous) -> (q [nq][n], converged u8 [n], iters i32 [n], resid [2][n]).
-        `out` may carry preallocated (q, converged, iters, resid) to keep the call allocation-free."""
+        `out` may carry preallocated (q, converged, iters, resid) to keep the call allocation-free.
+        `kernel`: None = launcher's choice by batch size, "lane" / "pair" force a thread mapping (same results)."""
         self._chk_dev(q_init, pose)
         if q_init.dtype != pose.dtype:
             raise TypeError("q_init and pose must share a dtype")
@@ -149,7 +154,7 @@ class GraspIK:
             resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
         else:
             q, conv, iters, resid = out
-        prm = self._params(eps, dt, max_iters, damping)
+        prm = self._params(eps, dt, max_iters, damping, kernel)
         f = getattr(self._lib, f"gik_solve_{_sfx(q_init.dtype)}")
         _cabi.check(f(self._h, n, self._ptr(q_init), self._ptr(pose), ctypes.byref(prm), self._ptr(q),
                       self._ptr(conv), self._ptr(iters), self._ptr(resid), self._stream()), "gik_solve")
@@ -171,17 +176,20 @@ class GraspIK:
         return qb, cb, wh
 
     def project_edges_soa(self, q_start, pose_a, pose_b, num_steps, max_steps: int, *, eps=EPSILON, dt=DT,
-                          max_iters=MAX_ITERS, damping=0.0):
+                          max_iters=MAX_ITERS, damping=0.0, kernel=None, out=None):
         """q_start [nq][E], pose_a/b [12][E], num_steps i32 [E] -> (q_path [max_steps][nq][E], n_valid i32 [E],
         iters_total i32 [E]).  Rows >= n_valid[e] of q_path are zero."""
         self._chk_dev(q_start, pose_a, pose_b, num_steps)
         E = q_start.shape[1]
         if num_steps.dtype != torch.int32:
             raise TypeError("num_steps must be int32")
-        path = torch.zeros((max_steps, self.nq, E), dtype=q_start.dtype, device=self.device)
-        nv = torch.empty((E,), dtype=torch.int32, device=self.device)
-        itt = torch.empty((E,), dtype=torch.int32, device=self.device)
-        prm = self._params(eps, dt, max_iters, damping)
+        if out is None:
+            path = torch.zeros((max_steps, self.nq, E), dtype=q_start.dtype, device=self.device)
+            nv = torch.empty((E,), dtype=torch.int32, device=self.device)
+            itt = torch.empty((E,), dtype=torch.int32, device=self.device)
+        else:
+            path, nv, itt = out
+        prm = self._params(eps, dt, max_iters, damping, kernel)
         f = getattr(self._lib, f"gik_project_edges_{_sfx(q_start.dtype)}")
         _cabi.check(f(self._h, E, max_steps, self._ptr(q_start.contiguous()), self._ptr(pose_a.contiguous()),
                       self._ptr(pose_b.contiguous()), self._ptr(num_steps.contiguous()), ctypes.byref(prm),
@@ -202,7 +210,7 @@ class GraspIK:
         return self.jac_soa(q.t().contiguous()).permute(3, 0, 1, 2)
 
     def solve(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
-              return_info=False):
+              return_info=False, kernel=None):
         """q_init [B,nq] (or [nq], broadcast), pose [B,12|4x4|7|3] -> (q [B,nq], converged bool [B][, SolveInfo])."""
         p12 = as_pose12(pose, dtype=dtype, device=self.device)
         B = p12.shape[0]
@@ -215,7 +223,7 @@ class GraspIK:
             B = qi.shape[0]
             p12 = p12.expand(B, 12)
         q, conv, iters, resid = self.solve_soa(qi.t().contiguous(), p12.t().contiguous(), eps=eps, dt=dt,
-                                               max_iters=max_iters, damping=damping)
+                                               max_iters=max_iters, damping=damping, kernel=kernel)
         res = (q.t(), conv.bool())
         if return_info:
             res = res + (SolveInfo(iters, resid.t()),)

@@ -52,7 +52,7 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
   DevTable<T> d;
   int rc = build_dev_table<T>(*tab, d);
   if (rc) return rc;
-  const T eps = (T)prm->eps, dt = (T)prm->dt, lambda = (T)prm->damping;
+  const T eps2 = (T)(prm->eps * prm->eps), dt = (T)prm->dt, lambda = (T)prm->damping;
   const bool generic = (prm->flags & 1) != 0;   // test hook: force the TZ = 0 instantiation
   for (int64_t i = 0; i < n; ++i) {
     T q[kActive], cube[12], tgt[2][12], dq[kActive], rL = 0, rR = 0;
@@ -66,7 +66,7 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
       // same specialisation rule as launch_solve() in csrc/gik_kernels.cu
       if ((d.tzero & kNextageTZ) == kNextageTZ && !generic) ik_iteration<T, true, kNextageTZ>(d, q, tgt, lambda, dq, rL, rR);
       else ik_iteration<T, true, 0>(d, q, tgt, lambda, dq, rL, rR);
-      ok = (rL < eps) && (rR < eps) && (it < prm->max_iters);
+      ok = (rL < eps2) && (rR < eps2) && (it < prm->max_iters);
       if (ok || it >= prm->max_iters) break;
       apply_step(d, q, dq, dt);
       ++it;
@@ -80,7 +80,7 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
     }
     conv[i] = ok ? 1 : 0;
     if (iters) iters[i] = it;
-    if (resid) { resid[i] = rL; resid[n + i] = rR; }
+    if (resid) { resid[i] = sqrt_(rL); resid[n + i] = sqrt_(rR); }
   }
   return 0;
 }

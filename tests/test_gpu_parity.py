@@ -205,6 +205,30 @@ def test_cabi_error_codes_on_device(solver):
     assert b.value % 148 == 0 and t.value == 128
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_pair_kernel_equals_lane_kernel(solver, dtype):
+    # the two thread mappings (problem per lane / problem per lane pair) run the same operations on the same values
+    n = 3001
+    P = _t(make_poses(n, 61), dtype).t().contiguous()
+    q0 = torch.zeros((15, n), dtype=dtype, device="cuda:0")
+    a = solver.solve_soa(q0, P, kernel="lane")
+    b = solver.solve_soa(q0, P, kernel="pair")
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    # and the launcher's own choice (small batch -> pair) is one of them
+    c = solver.solve_soa(q0, P)
+    assert torch.equal(c[0], a[0])
+    # edge mode
+    E, S = 64, 5
+    A = make_poses(E, 62, "sampler"); B = A.copy(); B[:, 9:] += np.random.default_rng(4).uniform(-0.06, 0.06, size=(E, 3))
+    qs, ok = solver.solve(torch.zeros(15), _t(A, dtype), dtype=dtype)
+    ns = torch.full((E,), S, dtype=torch.int32, device="cuda:0")
+    args = (qs.t().contiguous(), _t(A, dtype).t().contiguous(), _t(B, dtype).t().contiguous(), ns, S)
+    pa = solver.project_edges_soa(*args, kernel="lane")
+    pb = solver.project_edges_soa(*args, kernel="pair")
+    assert torch.equal(pa[1], pb[1]) and torch.equal(pa[2], pb[2]) and torch.equal(pa[0], pb[0])
+
+
 # ----------------------------------------------------------------------------------------------------------
 # K4 / config 3: best-of restarts
 # ----------------------------------------------------------------------------------------------------------
