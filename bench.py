@@ -28,6 +28,7 @@ N_PER_GPU = 1 << 20
 WORKSPACE_LO = (0.20, -0.40, 0.93)
 WORKSPACE_HI = (0.60, 0.40, 1.40)
 METRIC = "dual-arm grasp IK solves/sec"
+_STDOUT = sys.stdout
 
 
 def parse():
@@ -44,6 +45,9 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 (default, the metric's workload), 3 restarts fp64, 4 edge projection, 5 sharded sweep")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the result all-gather")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = the solve kernel stores results into every rank's symmetric-memory arrays over "
+                         "NVLink (falls back to nccl if symmetric memory is unavailable); 'nccl' = all_gather_into_tensor")
     ap.add_argument("--kernel", default=None, choices=["lane", "pair"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
@@ -113,7 +117,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -328,8 +332,24 @@ def run_b200(args):
         wl.name = f"config5: {total} config-2 problems sharded over {world} GPU(s) + all-gather of q/converged; " + wl.name
         scaling = "strong"
     wl.kernel_choice = args.kernel
-    gather = world > 1 and not args.no_gather
-    n_total_gather = wl.solves * world
+    gather = world > 1 and not args.no_gather and args.config in (2, 5)
+    if args.config == 5:
+        n_total_gather, gather_off = total, lo_i
+    else:
+        n_total_gather, gather_off = wl.solves * world, wl.solves * rank
+    fused = None
+    collective = "none"
+    if gather:
+        collective = "all_gather_into_tensor (NCCL) of q [15][n] + converged [n] per step"
+        if args.gather == "fused":
+            try:
+                fused = gdist.SymmetricResults(15, n_total_gather, dtype, dev)
+                fused_out = (wl.out[2], wl.out[3])
+                collective = ("fused: the solve kernel's epilogue stores q/converged into every rank's symmetric-memory "
+                              "result arrays over NVLink (P2P st.global), then one cross-rank barrier per step")
+            except Exception as e:      # symmetric memory unavailable on this box: keep the NCCL gather and say so
+                fused = None
+                collective += f" (fused path unavailable: {type(e).__name__})"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -341,10 +361,16 @@ def run_b200(args):
         flush.fill_(1)                                       # L2 flush between iterations
         if ev:
             ev[0].record()
-        q, conv = wl.launch()
+        if fused is not None:
+            solver.solve_scatter_soa(wl.q0, wl.pose, fused.q_ptrs, fused.conv_ptrs, n_total_gather,
+                                     gather_off, out=fused_out, kernel=args.kernel)
+        else:
+            q, conv = wl.launch()
         if ev:
             ev[1].record()
-        if gather and args.config in (2, 5):
+        if fused is not None:
+            fused.barrier()
+        elif gather:
             gdist.all_gather_results(q, conv, n_total_gather)
 
     for _ in range(max(args.warmup, 0)):
@@ -367,6 +393,8 @@ def run_b200(args):
     barrier()
     if sampler:
         sampler.stop()
+    if fused is not None:     # the local flags live in the symmetric array: bring this rank's slab back for the stats
+        wl.out[1].copy_(fused.conv[gather_off:gather_off + wl.solves])
     ms_total = e0.elapsed_time(e1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / max(args.steps, 1)
     launches = solver.launches - launches0
@@ -464,7 +492,7 @@ def run_b200(args):
 
     cfg = {"workload": wl.name, "problems_per_gpu_per_step": solves_all / world,
            "l2": "256 MB flush write before every step (inside the timed region)",
-           "collective": ("all_gather of q [15][n] + converged [n] per step" if gather and args.config in (2, 5) else "none"),
+           "collective": collective,
            "converged_fraction": conv_frac, "mean_iterations": iters_sum / solves_all}
     cfg.update(extra)
     line = {
@@ -476,12 +504,18 @@ def run_b200(args):
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # Exactly ONE line on stdout: libraries (NCCL prints its version banner there) are routed to stderr for the whole
+    # run and the JSON line goes to the saved descriptor.
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -110,6 +110,23 @@ int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double*
                   const gik_params_t* params, double* q_out, uint8_t* converged, int32_t* iters,
                   double* resid, void* stream);
 
+/* K3 fused with its all-gather (multi-GPU): the same solve, but each rank's kernel stores its
+ * results straight into the result arrays of ALL ranks through peer-mapped pointers (NVLink / NVSwitch P2P stores from
+ * the kernel's epilogue), so no collective follows the kernel.  q_all[p] / conv_all[p] are HOST arrays of n_peers
+ * device pointers, valid on this handle's device (this rank's own buffer and the peer mappings of the others, e.g.
+ * CUDA IPC or torch symmetric memory): rank p's q array [nq][n_total] and flag array [n_total].  This rank's problem i
+ * lands in column offset + i of every array.  iters [n] / resid [2][n] stay local and may be NULL.  The caller
+ * provides the cross-rank barrier after the launch (results are visible to a peer once this stream has passed it). */
+#define GIK_MAX_PEERS 16
+int gik_solve_scatter_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose,
+                          const gik_params_t* params, int32_t n_peers, float* const* q_all,
+                          uint8_t* const* conv_all, int64_t n_total, int64_t offset, int32_t* iters, float* resid,
+                          void* stream);
+int gik_solve_scatter_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose,
+                          const gik_params_t* params, int32_t n_peers, double* const* q_all,
+                          uint8_t* const* conv_all, int64_t n_total, int64_t offset, int32_t* iters, double* resid,
+                          void* stream);
+
 /* K4. Best-of-restarts reduction (new; BASELINE config 3).  Problem (p, r) of a [n_place x n_restart]
  * solve is stored at index p * n_restart + r.  Picks, per placement, the converged candidate with the
  * smallest max(resid_L, resid_R); ties -> lowest restart index; if none converged, the smallest

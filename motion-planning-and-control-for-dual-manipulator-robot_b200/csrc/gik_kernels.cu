@@ -39,8 +39,13 @@ struct SolveArgs {
   // batch mode
   const T* q_init;      // [nq][n]
   const T* pose;        // [12][n]   (edges: pose_a)
-  T* q_out;             // [nq][n]   (edges: q_path [max_steps][nq][n])
-  uint8_t* conv;        // [n]
+  T* q_out;             // edges: q_path [max_steps][nq][n]   (batch mode stores through q_dst / conv_dst)
+  // batch-mode destinations: 1 (the caller's q_out / converged) or, for the fused all-gather, one per rank
+  // (peer-mapped pointers); a result goes to column out_off + idx of arrays with out_n columns
+  T* q_dst[GIK_MAX_PEERS];
+  uint8_t* conv_dst[GIK_MAX_PEERS];
+  int32_t n_dst;
+  int64_t out_n, out_off;
   int32_t* iters;       // [n] or null (edges: iters_total)
   T* resid;             // [2][n] or null
   // edge mode
@@ -143,15 +148,19 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     } else if (active) {
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
+        const int64_t col = a.out_off + idx;
+        for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
+          T* qo = a.q_dst[d];
 #pragma unroll
-        for (int i = 0; i < kActive; ++i) a.q_out[(int64_t)tab.act_q[i] * n + idx] = q[i];
-        for (int p = 0; p < tab.n_passive; ++p) {
-          const int j = tab.passive_q[p];
-          T v = __ldg(a.q_init + (int64_t)j * n + idx);
-          if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
-          a.q_out[(int64_t)j * n + idx] = v;
+          for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_n + col] = q[i];
+          for (int p = 0; p < tab.n_passive; ++p) {
+            const int j = tab.passive_q[p];
+            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
+            qo[(int64_t)j * a.out_n + col] = v;
+          }
+          a.conv_dst[d][col] = ok ? 1 : 0;
         }
-        a.conv[idx] = ok ? 1 : 0;
         if (a.iters) a.iters[idx] = it;
         if (a.resid) { a.resid[idx] = sqrt_(rL); a.resid[n + idx] = sqrt_(rR); }
         active = false;
@@ -292,22 +301,27 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       const bool batch = (MODE == MODE_BATCH);
       if (!batch) it_total += it;
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
-        T* dst = batch ? a.q_out : a.q_out + (int64_t)(step - 1) * tab.nq * n;
         const bool moved = batch ? (it > 0) : (it_total > 0);
+        const int n_dst = batch ? a.n_dst : 1;
+        const int64_t ld = batch ? a.out_n : n, col = batch ? a.out_off + idx : idx;
+        for (int d = 0; d < n_dst; ++d) {       // batch: 1 destination, or every rank's result array (fused all-gather)
+          T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * n + idx] = q[1 + k];
-        if (h == 0) {
-          dst[(int64_t)tab.act_q[0] * n + idx] = q[0];
-          for (int p = 0; p < tab.n_passive; ++p) {
-            const int j = tab.passive_q[p];
-            T v = __ldg(a.q_init + (int64_t)j * n + idx);
-            if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
-            dst[(int64_t)j * n + idx] = v;
+          for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col] = q[1 + k];
+          if (h == 0) {
+            dst[(int64_t)tab.act_q[0] * ld + col] = q[0];
+            for (int p = 0; p < tab.n_passive; ++p) {
+              const int j = tab.passive_q[p];
+              T v = __ldg(a.q_init + (int64_t)j * n + idx);
+              if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
+              dst[(int64_t)j * ld + col] = v;
+            }
+            if (batch) a.conv_dst[d][col] = ok ? 1 : 0;
           }
         }
       }
       if (batch) {
-        if (h == 0) { a.conv[idx] = ok ? 1 : 0; if (a.iters) a.iters[idx] = it; }
+        if (h == 0 && a.iters) a.iters[idx] = it;
         if (a.resid) a.resid[(int64_t)h * n + idx] = sqrt_(r);
         active = false;
       } else if (ok && step < nsteps) {
@@ -552,7 +566,29 @@ int solve_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const g
   if (n == 0) return GIK_OK;
   if (!q_init || !pose || !q_out || !conv) return GIK_E_NULL;
   SolveArgs<T> a{};
-  a.q_init = q_init; a.pose = pose; a.q_out = q_out; a.conv = conv; a.iters = iters; a.resid = resid;
+  a.q_init = q_init; a.pose = pose; a.iters = iters; a.resid = resid;
+  a.q_dst[0] = q_out; a.conv_dst[0] = conv; a.n_dst = 1; a.out_n = n; a.out_off = 0;
+  a.n = n;
+  return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+}
+
+template <typename T>
+int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, int32_t n_peers,
+                T* const* q_all, uint8_t* const* conv_all, int64_t n_total, int64_t offset, int32_t* iters, T* resid,
+                void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0 || n_peers < 1 || n_peers > GIK_MAX_PEERS || offset < 0 || n_total < 0 || offset + n > n_total) return GIK_E_SIZE;
+  int rc = check_params(prm);
+  if (rc) return rc;
+  if (n == 0) return GIK_OK;
+  if (!q_init || !pose || !q_all || !conv_all) return GIK_E_NULL;
+  SolveArgs<T> a{};
+  a.q_init = q_init; a.pose = pose; a.iters = iters; a.resid = resid;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!q_all[p] || !conv_all[p]) return GIK_E_NULL;
+    a.q_dst[p] = q_all[p]; a.conv_dst[p] = conv_all[p];
+  }
+  a.n_dst = n_peers; a.out_n = n_total; a.out_off = offset;
   a.n = n;
   return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
 }
@@ -693,6 +729,17 @@ int gik_solve_f32(gik_handle_t h, int64_t n, const float* q_init, const float* p
 int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p,
                   double* q_out, uint8_t* conv, int32_t* iters, double* resid, void* s) {
   return solve_api<double>(h, n, q_init, pose, p, q_out, conv, iters, resid, s);
+}
+
+int gik_solve_scatter_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p,
+                          int32_t n_peers, float* const* q_all, uint8_t* const* conv_all, int64_t n_total, int64_t offset,
+                          int32_t* iters, float* resid, void* s) {
+  return scatter_api<float>(h, n, q_init, pose, p, n_peers, q_all, conv_all, n_total, offset, iters, resid, s);
+}
+int gik_solve_scatter_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p,
+                          int32_t n_peers, double* const* q_all, uint8_t* const* conv_all, int64_t n_total, int64_t offset,
+                          int32_t* iters, double* resid, void* s) {
+  return scatter_api<double>(h, n, q_init, pose, p, n_peers, q_all, conv_all, n_total, offset, iters, resid, s);
 }
 
 int gik_best_of_f32(gik_handle_t h, int64_t n_place, int32_t n_restart, const float* q, const uint8_t* conv,

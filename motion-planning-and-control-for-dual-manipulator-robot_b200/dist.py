@@ -1,6 +1,10 @@
 """Multi-GPU: plain data partitioning of the batch (every IK problem is independent) -- one
-process per GPU, contiguous slab per rank, no collective on the data path -- followed by ONE all-gather of the
-results (q, converged) over NCCL / NVLink when the caller wants every rank to hold the whole answer."""
+process per GPU, contiguous slab per rank, no collective on the data path.  When every rank needs the whole answer:
+
+  * `all_gather_results`  -- ONE NCCL all-gather of (q, converged) after the kernel (the baseline), or
+  * `SymmetricResults` + `solve_sharded_fused` -- the solve kernel's own epilogue stores each result into every
+    rank's result array through NVLink peer mappings (torch symmetric memory), so no collective follows the kernel:
+    only a cross-rank barrier."""
 from __future__ import annotations
 
 import torch
@@ -51,3 +55,37 @@ def solve_sharded(solver, q_init_soa, pose_soa, n_total: int, *, gather=True, gr
         return q, conv, iters, resid
     qg, cg = all_gather_results(q, conv, n_total, group)
     return qg, cg, iters, resid
+
+
+class SymmetricResults:
+    """Result arrays q [nq][n_total] and converged u8 [n_total] allocated as torch symmetric memory: every rank maps
+    every other rank's copy, and the fused kernel (gik_solve_scatter_*) writes into all of them.
+    Reuse: call `barrier()` again before the next launch overwrites arrays a peer may still be reading."""
+
+    def __init__(self, nq: int, n_total: int, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.n_total, self.nq = int(n_total), int(nq)
+        self.q = symm_mem.empty((nq, n_total), dtype=dtype, device=device)
+        self.conv = symm_mem.empty((n_total,), dtype=torch.uint8, device=device)
+        self._hq = symm_mem.rendezvous(self.q, group)
+        self._hc = symm_mem.rendezvous(self.conv, group)
+        self.q_ptrs = [int(p) for p in self._hq.buffer_ptrs]
+        self.conv_ptrs = [int(p) for p in self._hc.buffer_ptrs]
+        self.rank, self.world = self._hq.rank, self._hq.world_size
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: once this stream has passed it, every rank's kernel launched before its
+        own barrier has completed, i.e. all peer stores into this rank's arrays have landed."""
+        self._hq.barrier()
+
+
+def solve_sharded_fused(solver, q_init_soa, pose_soa, results: SymmetricResults, *, group=None, **kw):
+    """Each rank solves its slab and its kernel scatters the results into every rank's `results` arrays; returns
+    (results.q, results.conv, iters_local, resid_local) after the barrier."""
+    lo, hi = shard_bounds(results.n_total, results.rank, results.world)
+    assert hi - lo == q_init_soa.shape[1], "local slab does not match shard_bounds"
+    iters, resid = solver.solve_scatter_soa(q_init_soa, pose_soa, results.q_ptrs, results.conv_ptrs, results.n_total,
+                                            lo, **kw)
+    results.barrier()
+    return results.q, results.conv, iters, resid

@@ -162,6 +162,36 @@ class GraspIK:
             self.launches += 1
         return q, conv, iters, resid
 
+    def solve_scatter_soa(self, q_init: torch.Tensor, pose: torch.Tensor, q_ptrs, conv_ptrs, n_total: int, offset: int,
+                          *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0, kernel=None, out=None):
+        """K3 fused with its all-gather (gik_solve_scatter_*): solve this rank's slab and store every result into the
+        result arrays of ALL ranks.  `q_ptrs` / `conv_ptrs`: device addresses (ints) of each rank's [nq][n_total] q
+        array and [n_total] flag array as mapped on THIS device (see dist.SymmetricResults).  Returns the local
+        (iters [n], resid [2][n]); the caller runs the cross-rank barrier."""
+        self._chk_dev(q_init, pose)
+        if not (q_init.is_contiguous() and pose.is_contiguous()) or q_init.dtype != pose.dtype:
+            raise ValueError("SoA inputs must be contiguous and share a dtype")
+        n = q_init.shape[1]
+        if q_init.shape[0] != self.nq or pose.shape != (12, n):
+            raise ValueError("expected q_init [nq][n] and pose [12][n]")
+        if len(q_ptrs) != len(conv_ptrs) or not q_ptrs:
+            raise ValueError("need one q and one flag pointer per rank")
+        if out is None:
+            iters = torch.empty((n,), dtype=torch.int32, device=self.device)
+            resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
+        else:
+            iters, resid = out
+        P = len(q_ptrs)
+        qa = (ctypes.c_void_p * P)(*[int(p) for p in q_ptrs])
+        ca = (ctypes.c_void_p * P)(*[int(p) for p in conv_ptrs])
+        prm = self._params(eps, dt, max_iters, damping, kernel)
+        f = getattr(self._lib, f"gik_solve_scatter_{_sfx(q_init.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(q_init), self._ptr(pose), ctypes.byref(prm), P, qa, ca, int(n_total),
+                      int(offset), self._ptr(iters), self._ptr(resid), self._stream()), "gik_solve_scatter")
+        if n:
+            self.launches += 1
+        return iters, resid
+
     def best_of_soa(self, q, conv, resid, n_place: int, n_restart: int):
         """Problem (p, r) at column p * n_restart + r.  -> (q_best [nq][n_place], conv u8, which i32)."""
         self._chk_dev(q, conv, resid)

@@ -229,6 +229,41 @@ def test_pair_kernel_equals_lane_kernel(solver, dtype):
     assert torch.equal(pa[1], pb[1]) and torch.equal(pa[2], pb[2]) and torch.equal(pa[0], pb[0])
 
 
+def test_scatter_entry_on_one_gpu(solver):
+    # gik_solve_scatter_* with two destination arrays on the SAME device standing in for two ranks: the slab lands at
+    # its column offset in both, other columns stay untouched, values equal the plain solve
+    n, n_total, off = 1000, 2500, 700
+    P = _t(make_poses(n, 71), torch.float32).t().contiguous()
+    q0 = torch.zeros((15, n), dtype=torch.float32, device="cuda:0")
+    ref = solver.solve_soa(q0, P, kernel="lane")
+    for kern in ("lane", "pair"):
+        qa = [torch.full((15, n_total), -7.0, device="cuda:0") for _ in range(2)]
+        ca = [torch.full((n_total,), 9, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
+        iters, resid = solver.solve_scatter_soa(q0, P, [t.data_ptr() for t in qa], [t.data_ptr() for t in ca], n_total, off,
+                                                kernel=kern)
+        for d in range(2):
+            assert torch.equal(qa[d][:, off:off + n], ref[0]) and torch.equal(ca[d][off:off + n], ref[1])
+            assert (qa[d][:, :off] == -7).all() and (qa[d][:, off + n:] == -7).all()
+            assert (ca[d][:off] == 9).all() and (ca[d][off + n:] == 9).all()
+        assert torch.equal(iters, ref[2]) and torch.equal(resid, ref[3])
+    from gik_b200 import _cabi
+    with pytest.raises(_cabi.GikError):                    # slab does not fit
+        solver.solve_scatter_soa(q0, P, [qa[0].data_ptr()], [ca[0].data_ptr()], n_total, n_total - 10)
+
+
+def test_fused_all_gather_two_gpus():
+    # NVLink path: needs >= 2 GPUs (gpurun --gpus 2); the single-GPU round-end run skips it
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(ROOT, "tests", "mp_fused_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "FUSED_OK" in r.stdout
+
+
 # ----------------------------------------------------------------------------------------------------------
 # K4 / config 3: best-of restarts
 # ----------------------------------------------------------------------------------------------------------
