@@ -42,6 +42,7 @@ extern "C" {
 #define GIK_E_TOPOLOGY        -4   /* table does not match the compiled torso + two 6R-arm fast path */
 #define GIK_E_PARAM           -5   /* bad solver parameter (eps<=0, dt<=0, max_iters<0, damping<0) */
 #define GIK_E_HANDLE          -6   /* bad or destroyed handle */
+#define GIK_E_NOSCENE         -7   /* collision entry called before gik_scene_attach */
 
 /* Host-side flattened kinematic model: what the reference obtains from
  * RobotWrapper.BuildFromURDF + translaterobot (setup_pinocchio.py:28-32,73-75) and from the cube's
@@ -154,6 +155,56 @@ int gik_project_edges_f64(gik_handle_t h, int64_t n_edges, int32_t max_steps, co
                           const double* pose_a, const double* pose_b, const int32_t* num_steps,
                           const gik_params_t* params, double* q_path, int32_t* n_valid,
                           int32_t* iters_total, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Collision predicate.  The reference's success flag is `converged and not collision(robot, q)`
+ * (inverse_geometry.py:70,97-98); path.py additionally filters samples on distanceToObstacle(robot, q) >= 0.04
+ * (path.py:61-62) and on the cube's own collisions with the table / obstacle (path.py:51-52, 145-146).
+ * gik_scene_t is the flattened collision model that setup_pinocchio.py:44-83 assembles: convex primitives attached
+ * to joints, plus the pair list after addAllCollisionPairs / SRDF removal / the extra obstacle-cube pair.
+ * ------------------------------------------------------------------------------------------------------- */
+#define GIK_MAX_GEOMS 64
+#define GIK_MAX_PAIRS 1024
+#define GIK_GEOM_BOX      0   /* size = half extents */
+#define GIK_GEOM_SPHERE   1   /* size[0] = radius */
+#define GIK_GEOM_CYLINDER 2   /* size[0] = radius, size[1] = half length, axis = local z */
+
+typedef struct gik_geom_s {
+  int32_t type;       /* GIK_GEOM_* */
+  int32_t joint;      /* q index of the parent joint, -1 = universe (GeometryObject.parentJoint - 1) */
+  double  R[9];       /* GeometryObject.placement in the parent joint frame, row-major */
+  double  p[3];
+  double  size[3];
+} gik_geom_t;
+
+typedef struct gik_scene_s {
+  int32_t n_geoms, n_pairs;
+  int32_t cube_geom;      /* geometry whose placement is replaced per problem (tools.setcubeplacement) */
+  int32_t table_geom;     /* 'baseLink_0' */
+  int32_t obstacle_geom;  /* 'obstaclebase_0' */
+  int32_t reserved;
+  gik_geom_t geoms[GIK_MAX_GEOMS];
+  uint8_t pair_a[GIK_MAX_PAIRS], pair_b[GIK_MAX_PAIRS];   /* robot.collision_model.collisionPairs */
+} gik_scene_t;
+
+/* Uploads the scene to the handle's device (replaces a previous one).  Returns GIK_E_SIZE / GIK_E_MODEL on a bad scene. */
+int gik_scene_attach(gik_handle_t h, const gik_scene_t* scene);
+
+/* Replaces tools.collision(robot, q) (tools.py:25-35) for n configurations: q [nq][n]; cube_pose [12][n] = placement
+ * of the cube geometry for each problem (what setcubeplacement wrote before the reference's call; NULL = the scene's
+ * own) -> colliding [n] (1 = at least one collision pair intersects). */
+int gik_collision_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, uint8_t* colliding, void* stream);
+int gik_collision_f64(gik_handle_t h, int64_t n, const double* q, const double* cube_pose, uint8_t* colliding, void* stream);
+
+/* Replaces `distanceToObstacle(robot, q) >= threshold` (tools.py:38-51 with path.py:61-62): clear [n] = 1 when every
+ * pair whose second geometry is the table or the obstacle is at least `threshold` apart. */
+int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, double threshold, uint8_t* clear, void* stream);
+int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube_pose, double threshold, uint8_t* clear, void* stream);
+
+/* Replaces the cube's own collision test of path.py:51-52 / 145-146 (cube vs table, cube vs obstacle):
+ * cube_pose [12][n] -> colliding [n]. */
+int gik_cube_collision_f32(gik_handle_t h, int64_t n, const float* cube_pose, uint8_t* colliding, void* stream);
+int gik_cube_collision_f64(gik_handle_t h, int64_t n, const double* cube_pose, uint8_t* colliding, void* stream);
 
 /* Measurement helpers (bench.py). */
 /* Algorithmic FLOPs of ONE descent iteration of ONE dual-arm problem (SURVEY.md 8d breakdown). */

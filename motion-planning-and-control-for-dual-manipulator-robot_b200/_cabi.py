@@ -30,7 +30,8 @@ class GikError(RuntimeError):
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in ("gik_kernels.cu", "gik_core.cuh", "gik_table.h")] + \
+    return [os.path.join(CSRC, f) for f in ("gik_kernels.cu", "gik_core.cuh", "gik_table.h", "gik_collide.cuh",
+                                            "gik_collide_impl.cuh")] + \
            [os.path.join(_HERE, "..", "include", "gik.h")]
 
 
@@ -87,6 +88,12 @@ def lib() -> ctypes.CDLL:
                                                             ctypes.POINTER(_P), _I64, _I64, _P, _P, _P]
         getattr(L, f"gik_best_of_{sfx}").argtypes = [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]
         getattr(L, f"gik_project_edges_{sfx}").argtypes = [_P, _I64, _I32, _P, _P, _P, _P, PP, _P, _P, _P, _P]
+    from .scene import GikScene
+    L.gik_scene_attach.argtypes = [_P, ctypes.POINTER(GikScene)]
+    for sfx in ("f32", "f64"):
+        getattr(L, f"gik_collision_{sfx}").argtypes = [_P, _I64, _P, _P, _P, _P]
+        getattr(L, f"gik_clearance_{sfx}").argtypes = [_P, _I64, _P, _P, ctypes.c_double, _P, _P]
+        getattr(L, f"gik_cube_collision_{sfx}").argtypes = [_P, _I64, _P, _P, _P]
     L.gik_flops_per_iter.restype = ctypes.c_size_t
     L.gik_bytes_per_solve.argtypes = [ctypes.c_int]; L.gik_bytes_per_solve.restype = ctypes.c_size_t
     L.gik_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
@@ -101,6 +108,8 @@ EXPORTS = [
     "gik_default_params", "gik_create", "gik_destroy",
     "gik_fk_f32", "gik_fk_f64", "gik_jac_f32", "gik_jac_f64", "gik_solve_f32", "gik_solve_f64",
     "gik_solve_scatter_f32", "gik_solve_scatter_f64", "gik_best_of_f32", "gik_best_of_f64", "gik_project_edges_f32", "gik_project_edges_f64",
+    "gik_scene_attach", "gik_collision_f32", "gik_collision_f64", "gik_clearance_f32", "gik_clearance_f64",
+    "gik_cube_collision_f32", "gik_cube_collision_f64",
     "gik_flops_per_iter", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",
     "gik_strerror", "gik_version",
 ]

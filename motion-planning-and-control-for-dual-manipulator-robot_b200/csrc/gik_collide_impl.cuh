@@ -1,0 +1,165 @@
+// gik_collide_impl.cuh -- collision kernels + their C ABI (included at the end of gik_kernels.cu: one translation
+// unit, one library).  Mapping: ONE CONFIGURATION PER WARP.  Lane 0 walks the kinematic tree into shared memory,
+// the lanes place the geometries (oMg = oMi[parent] * placement, pin.updateGeometryPlacements), then the collision
+// pairs are dealt round-robin to the 32 lanes: bounding-sphere rejection first, boolean GJK on the survivors, one
+// __any_sync per round for the early exit.  The scene (geometries, pair lists) lives in global memory and is read
+// through the read-only path; per-configuration traffic is q in (60 B) and one flag out.
+#pragma once
+#include "gik_collide.cuh"
+
+namespace gik {
+
+constexpr int kCollideWarps = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kCollideWarps * 32)
+gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pb,
+                     int n_pairs, int64_t n, const T* __restrict__ q, const T* __restrict__ cube_pose, T margin,
+                     uint8_t* __restrict__ out, int invert) {
+  __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
+  __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nq = sc->tree.nq, ng = sc->n_geoms;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    if (q && lane == 0) {
+      for (int j = 0; j < nq; ++j) {
+        const int par = sc->tree.parent[j];
+        joint_placement(sc->tree, j, par < 0 ? (const T*)nullptr : &s_oMi[w][par][0], __ldg(q + (int64_t)j * n + i),
+                        &s_oMi[w][j][0]);
+      }
+    }
+    __syncwarp();
+    for (int g = lane; g < ng; g += 32) {
+      const DevGeom<T>& G = sc->g[g];
+      T P[12];
+      if (g == sc->cube_geom && cube_pose) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = __ldg(cube_pose + (int64_t)k * n + i);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P[k] = G.R[k];
+        P[9] = G.p[0]; P[10] = G.p[1]; P[11] = G.p[2];
+      }
+      if (G.joint >= 0 && q) se3_mul12(&s_oMi[w][G.joint][0], P, &s_oMg[w][g][0]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_oMg[w][g][k] = P[k];
+      }
+    }
+    __syncwarp();
+    bool hit = false;
+    for (int k0 = 0; k0 < n_pairs; k0 += 32) {
+      const int k = k0 + lane;
+      if (k < n_pairs) {
+        const int a = pa[k], b = pb[k];
+        hit = pair_hits(sc->g[a], &s_oMg[w][a][0], sc->g[b], &s_oMg[w][b][0], margin);
+      }
+      if (__any_sync(0xffffffffu, hit)) { hit = true; break; }
+    }
+    if (lane == 0) out[i] = (uint8_t)((hit ? 1 : 0) ^ (invert ? 1 : 0));
+    __syncwarp();
+  }
+}
+
+}  // namespace gik
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct gik_scene_dev {
+  gik::DevScene<float>* sc32 = nullptr;
+  gik::DevScene<double>* sc64 = nullptr;
+  uint8_t* pairs = nullptr;   // [3 lists][2][GIK_MAX_PAIRS]: all pairs | table/obstacle pairs | cube vs table, obstacle
+  int n_list[3] = {0, 0, 0};
+};
+
+namespace {
+
+void free_scene(gik_scene_dev* sd) {
+  if (!sd) return;
+  cudaFree(sd->sc32); cudaFree(sd->sc64); cudaFree(sd->pairs);
+  delete sd;
+}
+
+template <typename T> gik::DevScene<T>* scene_of(gik_scene_dev* sd);
+template <> gik::DevScene<float>* scene_of<float>(gik_scene_dev* sd) { return sd->sc32; }
+template <> gik::DevScene<double>* scene_of<double>(gik_scene_dev* sd) { return sd->sc64; }
+
+// list: 0 all pairs, 1 table/obstacle pairs, 2 cube's own pairs
+template <typename T>
+int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int list, double margin, int invert,
+                uint8_t* out, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0) return GIK_E_SIZE;
+  if (!(margin >= 0.0)) return GIK_E_PARAM;
+  if (!h->scene) return GIK_E_NOSCENE;
+  if (n == 0) return GIK_OK;
+  if (!out || (list != 2 && !q) || (list == 2 && !cube_pose)) return GIK_E_NULL;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  gik_scene_dev* sd = h->scene;
+  int64_t blocks = (n + gik::kCollideWarps - 1) / gik::kCollideWarps;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  const uint8_t* pa = sd->pairs + (size_t)list * 2 * GIK_MAX_PAIRS;
+  gik::gik_collision_kernel<T><<<(int)blocks, gik::kCollideWarps * 32, 0, (cudaStream_t)stream>>>(
+      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)margin, out, invert);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gik_scene_attach(gik_handle_t h, const gik_scene_t* scene) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (!scene) return GIK_E_NULL;
+  int rc = gik::validate_scene(h->host, *scene);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  gik_scene_dev* sd = new (std::nothrow) gik_scene_dev();
+  if (!sd) return (int)cudaErrorMemoryAllocation;
+  gik::DevScene<float>* h32 = new (std::nothrow) gik::DevScene<float>();
+  gik::DevScene<double>* h64 = new (std::nothrow) gik::DevScene<double>();
+  uint8_t* hp = new (std::nothrow) uint8_t[3 * 2 * GIK_MAX_PAIRS]();
+  cudaError_t e = (h32 && h64 && hp) ? cudaSuccess : cudaErrorMemoryAllocation;
+  if (e == cudaSuccess) {
+    gik::fill_dev_scene(h->host, *scene, *h32);
+    gik::fill_dev_scene(h->host, *scene, *h64);
+    for (int k = 0; k < scene->n_pairs; ++k) {
+      const uint8_t a = scene->pair_a[k], b = scene->pair_b[k];
+      hp[sd->n_list[0]] = a; hp[GIK_MAX_PAIRS + sd->n_list[0]++] = b;
+      if ((int)b == scene->table_geom || (int)b == scene->obstacle_geom) {          // tools.py:42
+        hp[2 * GIK_MAX_PAIRS + sd->n_list[1]] = a; hp[3 * GIK_MAX_PAIRS + sd->n_list[1]++] = b;
+      }
+    }
+    const int env[2] = {scene->table_geom, scene->obstacle_geom};                    // setup_pinocchio.py:66-70
+    for (int k = 0; k < 2; ++k)
+      if (env[k] >= 0 && scene->cube_geom >= 0) {
+        hp[4 * GIK_MAX_PAIRS + sd->n_list[2]] = (uint8_t)env[k]; hp[5 * GIK_MAX_PAIRS + sd->n_list[2]++] = (uint8_t)scene->cube_geom;
+      }
+    if ((e = cudaMalloc(&sd->sc32, sizeof(*h32))) == cudaSuccess &&
+        (e = cudaMalloc(&sd->sc64, sizeof(*h64))) == cudaSuccess &&
+        (e = cudaMalloc(&sd->pairs, 3 * 2 * GIK_MAX_PAIRS)) == cudaSuccess &&
+        (e = cudaMemcpy(sd->sc32, h32, sizeof(*h32), cudaMemcpyHostToDevice)) == cudaSuccess &&
+        (e = cudaMemcpy(sd->sc64, h64, sizeof(*h64), cudaMemcpyHostToDevice)) == cudaSuccess)
+      e = cudaMemcpy(sd->pairs, hp, 3 * 2 * GIK_MAX_PAIRS, cudaMemcpyHostToDevice);
+  }
+  delete h32; delete h64; delete[] hp;
+  if (e != cudaSuccess) { free_scene(sd); return (int)e; }
+  cudaDeviceSynchronize();          // a previous scene may still be in use by enqueued kernels
+  free_scene(h->scene);
+  h->scene = sd;
+  return GIK_OK;
+}
+
+int gik_collision_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 0, 0.0, 0, out, s); }
+int gik_collision_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 0, 0.0, 0, out, s); }
+int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double thr, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 1, thr, 1, out, s); }
+int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double thr, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 1, thr, 1, out, s); }
+int gik_cube_collision_f32(gik_handle_t h, int64_t n, const float* cube, uint8_t* out, void* s) { return collide_api<float>(h, n, (const float*)nullptr, cube, 2, 0.0, 0, out, s); }
+int gik_cube_collision_f64(gik_handle_t h, int64_t n, const double* cube, uint8_t* out, void* s) { return collide_api<double>(h, n, (const double*)nullptr, cube, 2, 0.0, 0, out, s); }
+
+}  // extern "C"

@@ -446,11 +446,13 @@ struct gik_handle_s {
   gik_table_t host;
   DevTable<float> tab32;
   DevTable<double> tab64;
+  struct gik_scene_dev* scene;       // collision scene (gik_scene_attach), or null
   unsigned long long* queues;        // device: kQueueSlots work-queue heads, one per launch in flight
   std::atomic<uint32_t> next_queue;
 };
 static constexpr uint32_t kQueueSlots = 1024;   // launches that may be in flight on one handle at once
 static constexpr uint32_t kMagic = 0x67696b31u;  // "gik1"
+static void gik_free_scene_of(gik_handle_s* h);
 
 namespace {
 
@@ -701,6 +703,7 @@ int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out) {
     if (g.err != cudaSuccess) { delete h; return (int)g.err; }
   }
   h->next_queue.store(0);
+  h->scene = nullptr;
   h->magic = kMagic;
   *out = h;
   return GIK_OK;
@@ -712,6 +715,7 @@ int gik_destroy(gik_handle_t h) {
   {
     DeviceGuard g(h->device);
     cudaFree(h->queues);
+    gik_free_scene_of(h);
   }
   delete h;
   return GIK_OK;
@@ -802,6 +806,7 @@ const char* gik_strerror(int code) {
     case GIK_E_TOPOLOGY: return "kinematic table does not match the compiled torso + two 6R-arm fast path";
     case GIK_E_PARAM: return "invalid solver parameter";
     case GIK_E_HANDLE: return "invalid handle";
+    case GIK_E_NOSCENE: return "no collision scene attached (gik_scene_attach)";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -811,3 +816,6 @@ const char* gik_strerror(int code) {
 const char* gik_version(void) { return "gik 0.1 (sm_100a)"; }
 
 }  // extern "C"
+
+#include "gik_collide_impl.cuh"
+static void gik_free_scene_of(gik_handle_s* h) { free_scene(h->scene); h->scene = nullptr; }

@@ -6,6 +6,7 @@
 
 #include "../../include/gik.h"
 #include "gik_core.cuh"
+#include "gik_collide.cuh"
 
 namespace gik {
 
@@ -113,6 +114,46 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
     if (!active[j]) d.passive_q[d.n_passive++] = j;
   }
   return GIK_OK;
+}
+
+// ---- collision scene (gik_scene_t -> DevScene<T>) ----
+inline int validate_scene(const gik_table_t& t, const gik_scene_t& s) {
+  if (s.n_geoms < 1 || s.n_geoms > GIK_MAX_GEOMS || s.n_pairs < 0 || s.n_pairs > GIK_MAX_PAIRS) return GIK_E_SIZE;
+  for (int g = 0; g < s.n_geoms; ++g) {
+    if (s.geoms[g].type < 0 || s.geoms[g].type > 2 || s.geoms[g].joint < -1 || s.geoms[g].joint >= t.nq) return GIK_E_MODEL;
+    if (!(s.geoms[g].size[0] > 0.0)) return GIK_E_MODEL;
+  }
+  for (int k = 0; k < s.n_pairs; ++k)
+    if (s.pair_a[k] >= s.n_geoms || s.pair_b[k] >= s.n_geoms) return GIK_E_MODEL;
+  const int special[3] = {s.cube_geom, s.table_geom, s.obstacle_geom};
+  for (int k = 0; k < 3; ++k)
+    if (special[k] < -1 || special[k] >= s.n_geoms) return GIK_E_MODEL;
+  return GIK_OK;
+}
+
+
+template <typename T>
+inline void fill_dev_scene(const gik_table_t& t, const gik_scene_t& s, DevScene<T>& d) {
+  memset(&d, 0, sizeof(d));
+  d.tree.nq = t.nq;
+  for (int i = 0; i < t.nq; ++i) {
+    d.tree.parent[i] = t.parent[i];
+    d.tree.axis[i] = t.axis[i];
+    for (int k = 0; k < 9; ++k) d.tree.jR[i][k] = (T)t.joint_R[i][k];
+    for (int k = 0; k < 3; ++k) d.tree.jp[i][k] = (T)t.joint_p[i][k];
+  }
+  d.n_geoms = s.n_geoms;
+  d.cube_geom = s.cube_geom;
+  for (int g = 0; g < s.n_geoms; ++g) {
+    DevGeom<T>& G = d.g[g];
+    for (int k = 0; k < 9; ++k) G.R[k] = (T)s.geoms[g].R[k];
+    for (int k = 0; k < 3; ++k) G.p[k] = (T)s.geoms[g].p[k];
+    G.s0 = (T)s.geoms[g].size[0]; G.s1 = (T)s.geoms[g].size[1]; G.s2 = (T)s.geoms[g].size[2];
+    G.type = s.geoms[g].type; G.joint = s.geoms[g].joint;
+    const double a = s.geoms[g].size[0], b = s.geoms[g].size[1], c = s.geoms[g].size[2];
+    const double r = G.type == GIK_GEOM_BOX ? sqrt(a * a + b * b + c * c) : G.type == GIK_GEOM_SPHERE ? a : sqrt(a * a + b * b);
+    G.bound = (T)(r * (1.0 + 1e-6));
+  }
 }
 
 }  // namespace gik

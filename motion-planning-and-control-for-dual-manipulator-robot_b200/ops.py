@@ -11,6 +11,7 @@ import torch
 
 from . import _cabi
 from .model import KinematicTable, nextage_table
+from .scene import CollisionScene, nextage_scene
 
 # Reference literals: EPSILON (config.py:22), DT / max_iters (inverse_geometry.py:53-54)
 EPSILON = 1e-3
@@ -227,6 +228,70 @@ class GraspIK:
         if E:
             self.launches += 1
         return path, nv, itt
+
+    # ------------------------------------------------------------------ collision predicate
+    def attach_scene(self, scene: CollisionScene | None = None) -> "GraspIK":
+        """Upload the flattened collision model (gik_scene_attach).  Default: the reference's scene."""
+        self.scene = scene if scene is not None else nextage_scene()
+        sc = self.scene.to_c()
+        _cabi.check(self._lib.gik_scene_attach(self._h, ctypes.byref(sc)), "gik_scene_attach")
+        return self
+
+    def _need_scene(self):
+        if getattr(self, "scene", None) is None:
+            self.attach_scene()
+
+    def collision_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None) -> torch.Tensor:
+        """tools.collision(robot, q) for every column: q [nq][n], cube_pose [12][n] (None = scene's cube placement)
+        -> colliding u8 [n]."""
+        self._need_scene()
+        self._chk_dev(q_soa, cube_pose_soa)
+        n = q_soa.shape[1]
+        out = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        f = getattr(self._lib, f"gik_collision_{_sfx(q_soa.dtype)}")
+        cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
+        _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(cp), self._ptr(out), self._stream()), "gik_collision")
+        if n:
+            self.launches += 1
+        return out
+
+    def clearance_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None, threshold: float = 0.04) -> torch.Tensor:
+        """distanceToObstacle(robot, q) >= threshold (tools.py:38-51, path.py:61-62) -> clear u8 [n]."""
+        self._need_scene()
+        self._chk_dev(q_soa, cube_pose_soa)
+        n = q_soa.shape[1]
+        out = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        f = getattr(self._lib, f"gik_clearance_{_sfx(q_soa.dtype)}")
+        cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
+        _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(cp), float(threshold), self._ptr(out),
+                      self._stream()), "gik_clearance")
+        if n:
+            self.launches += 1
+        return out
+
+    def cube_collision_soa(self, cube_pose_soa: torch.Tensor) -> torch.Tensor:
+        """The cube's own collision test (cube vs table / obstacle, path.py:51-52): cube_pose [12][n] -> u8 [n]."""
+        self._need_scene()
+        self._chk_dev(cube_pose_soa)
+        n = cube_pose_soa.shape[1]
+        out = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        f = getattr(self._lib, f"gik_cube_collision_{_sfx(cube_pose_soa.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(cube_pose_soa.contiguous()), self._ptr(out), self._stream()), "gik_cube_collision")
+        if n:
+            self.launches += 1
+        return out
+
+    def collision(self, q, cube_pose=None, *, dtype=None) -> torch.Tensor:
+        """Row-major convenience: q [B,nq] (or [nq]), cube_pose [B,12|4x4|7|3] or None -> colliding bool [B]."""
+        qt = torch.as_tensor(q, device=self.device)
+        dtype = dtype or (qt.dtype if qt.dtype in (torch.float32, torch.float64) else torch.float64)
+        qt = qt.to(dtype)
+        if qt.dim() == 1:
+            qt = qt.unsqueeze(0)
+        cp = None
+        if cube_pose is not None:
+            cp = as_pose12(cube_pose, dtype=dtype, device=self.device, batch=qt.shape[0]).t().contiguous()
+        return self.collision_soa(qt.t().contiguous(), cp).bool()
 
     # ------------------------------------------------------------------ row-major convenience ([B, ...])
     def fk(self, q: torch.Tensor):

@@ -32,8 +32,8 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "grasp_ik_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("grasp_ik_oracle.c", "collision_oracle.inc")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", f"OUT={LIB}"], check=True, capture_output=True)
     return LIB
 
@@ -91,6 +91,29 @@ def project_edges(table_c, q_start, pose_a, pose_b, num_steps, max_steps, eps=1e
                             _p(pose_b), _p(ns), ctypes.c_double(eps), ctypes.c_double(dt), ctypes.c_int(max_iters),
                             ctypes.c_int(threads), _p(path), _p(nv), _p(itt))
     return path, nv, itt
+
+
+def scene_distance(table_c, scene_c, q, cube_pose=None, mode=0, cull=0.0, threads=0):
+    """Minimum pair distance per configuration (0 = collision).  mode 0: all pairs (tools.collision), 1: table/obstacle
+    pairs (tools.distanceToObstacle), 2: cube vs table/obstacle (path.py:51-52; q may be None)."""
+    if q is not None:
+        q = _c(q); n = q.shape[0]
+    else:
+        cube_pose = _c(cube_pose); n = cube_pose.shape[0]
+    cp = _c(cube_pose) if cube_pose is not None else None
+    out = np.empty(n)
+    L = lib()
+    L.orc_scene_distance(ctypes.byref(table_c), ctypes.byref(scene_c), ctypes.c_int64(n), _p(q) if q is not None else None,
+                         _p(cp) if cp is not None else None, ctypes.c_int(mode), ctypes.c_double(cull),
+                         ctypes.c_int(threads), _p(out))
+    return out
+
+
+def pair_distance(type_a, Ra, pa, sa, type_b, Rb, pb, sb):
+    L = lib()
+    L.orc_pair_distance.restype = ctypes.c_double
+    a = [_c(np.asarray(x, float).reshape(-1)) for x in (Ra, pa, sa, Rb, pb, sb)]
+    return L.orc_pair_distance(ctypes.c_int(type_a), _p(a[0]), _p(a[1]), _p(a[2]), ctypes.c_int(type_b), _p(a[3]), _p(a[4]), _p(a[5]))
 
 
 def max_threads():

@@ -359,6 +359,8 @@ int orc_project_edges(const orc_table_t* t, int64_t n, int max_steps, const doub
   return 0;
 }
 
+#include "collision_oracle.inc"
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

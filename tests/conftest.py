@@ -57,7 +57,7 @@ class HostSim:
         src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
         out = os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim.so")
         deps = [src] + [os.path.join(ROOT, "motion-planning-and-control-for-dual-manipulator-robot_b200", "csrc", f)
-                        for f in ("gik_core.cuh", "gik_table.h")] + [os.path.join(ROOT, "include", "gik.h")]
+                        for f in ("gik_core.cuh", "gik_table.h", "gik_collide.cuh")] + [os.path.join(ROOT, "include", "gik.h")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
@@ -96,6 +96,36 @@ class HostSim:
         assert f(ctypes.byref(tc), ctypes.c_int64(n), self._p(q0), self._p(pose), ctypes.byref(prm), self._p(q),
                  self._p(c), self._p(it), self._p(r)) == 0
         return q.T, c.astype(bool), it, r.T
+
+
+    def collide(self, tc, sc, q_rows, cube_rows, dtype, mode=0, margin=0.0):
+        """mode 0: collision(q); 1: some table/obstacle pair closer than `margin`; 2: cube vs table/obstacle."""
+        f = self.lib.hostsim_collide_f32 if dtype == np.float32 else self.lib.hostsim_collide_f64
+        q = None if q_rows is None else np.ascontiguousarray(np.asarray(q_rows, dtype).T)
+        cube = None if cube_rows is None else np.ascontiguousarray(np.asarray(cube_rows, dtype).T)
+        n = q.shape[1] if q is not None else cube.shape[1]
+        out = np.zeros(n, np.uint8)
+        rc = f(ctypes.byref(tc), ctypes.byref(sc), ctypes.c_int64(n), None if q is None else self._p(q),
+               None if cube is None else self._p(cube), ctypes.c_int(mode), ctypes.c_double(margin), self._p(out))
+        assert rc == 0, rc
+        return out.astype(bool)
+
+    def pair(self, ta, Ra, pa, sa, tb, Rb, pb, sb, dtype, margin=0.0):
+        f = self.lib.hostsim_pair_f32 if dtype == np.float32 else self.lib.hostsim_pair_f64
+        a = [np.ascontiguousarray(np.asarray(x, float).reshape(-1)) for x in (Ra, pa, sa, Rb, pb, sb)]
+        return bool(f(ctypes.c_int(ta), self._p(a[0]), self._p(a[1]), self._p(a[2]), ctypes.c_int(tb), self._p(a[3]),
+                      self._p(a[4]), self._p(a[5]), ctypes.c_double(margin)))
+
+
+@pytest.fixture(scope="session")
+def scene():
+    import gik_b200
+    return gik_b200.nextage_scene()
+
+
+@pytest.fixture(scope="session")
+def scene_c(scene):
+    return scene.to_c()
 
 
 @pytest.fixture(scope="session")

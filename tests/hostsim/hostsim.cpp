@@ -85,7 +85,59 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
   return 0;
 }
 
+// collision predicate, sequential over pairs (the kernel deals the same pairs to the lanes of a warp)
+template <typename T>
+static int collide_impl(const gik_table_t* tab, const gik_scene_t* scn, int64_t n, const T* q, const T* cube, int list,
+                        double margin, uint8_t* out) {
+  int rc = validate_table(*tab);
+  if (rc == 0) rc = validate_scene(*tab, *scn);
+  if (rc) return rc;
+  static DevScene<T> sc;
+  fill_dev_scene(*tab, *scn, sc);
+  for (int64_t i = 0; i < n; ++i) {
+    T oMi[GIK_MAX_NQ][12], oMg[GIK_MAX_GEOMS][12];
+    if (q)
+      for (int j = 0; j < sc.tree.nq; ++j)
+        joint_placement(sc.tree, j, sc.tree.parent[j] < 0 ? (const T*)nullptr : oMi[sc.tree.parent[j]], q[(int64_t)j * n + i], oMi[j]);
+    for (int g = 0; g < sc.n_geoms; ++g) {
+      T P[12];
+      for (int k = 0; k < 9; ++k) P[k] = sc.g[g].R[k];
+      for (int k = 0; k < 3; ++k) P[9 + k] = sc.g[g].p[k];
+      if (g == sc.cube_geom && cube) for (int k = 0; k < 12; ++k) P[k] = cube[(int64_t)k * n + i];
+      if (sc.g[g].joint >= 0 && q) se3_mul12(oMi[sc.g[g].joint], P, oMg[g]);
+      else for (int k = 0; k < 12; ++k) oMg[g][k] = P[k];
+    }
+    bool hit = false;
+    const int np = list == 2 ? 2 : scn->n_pairs;
+    for (int k = 0; k < np && !hit; ++k) {
+      int a, b;
+      if (list == 2) { a = k == 0 ? scn->table_geom : scn->obstacle_geom; b = scn->cube_geom; }
+      else { a = scn->pair_a[k]; b = scn->pair_b[k]; }
+      if (list == 1 && b != scn->table_geom && b != scn->obstacle_geom) continue;
+      hit = pair_hits(sc.g[a], oMg[a], sc.g[b], oMg[b], (T)margin);
+    }
+    out[i] = hit ? 1 : 0;
+  }
+  return 0;
+}
+
+// one pair of placed shapes: (type, R[9], p[3], size[3]) x 2 -> intersects?
+template <typename T>
+static int pair_impl(int ta, const double* Ra, const double* pa, const double* sa, int tb, const double* Rb, const double* pb,
+                     const double* sb, double margin) {
+  Shape<T> A, B;
+  for (int k = 0; k < 9; ++k) { A.R[k] = (T)Ra[k]; B.R[k] = (T)Rb[k]; }
+  A.p = {(T)pa[0], (T)pa[1], (T)pa[2]}; B.p = {(T)pb[0], (T)pb[1], (T)pb[2]};
+  A.s0 = (T)sa[0]; A.s1 = (T)sa[1]; A.s2 = (T)sa[2]; A.type = ta;
+  B.s0 = (T)sb[0]; B.s1 = (T)sb[1]; B.s2 = (T)sb[2]; B.type = tb;
+  return gjk_intersect(A, B, (T)margin) ? 1 : 0;
+}
+
 extern "C" {
+int hostsim_collide_f32(const gik_table_t* t, const gik_scene_t* s, int64_t n, const float* q, const float* cube, int list, double m, uint8_t* o) { return collide_impl<float>(t, s, n, q, cube, list, m, o); }
+int hostsim_collide_f64(const gik_table_t* t, const gik_scene_t* s, int64_t n, const double* q, const double* cube, int list, double m, uint8_t* o) { return collide_impl<double>(t, s, n, q, cube, list, m, o); }
+int hostsim_pair_f32(int ta, const double* Ra, const double* pa, const double* sa, int tb, const double* Rb, const double* pb, const double* sb, double m) { return pair_impl<float>(ta, Ra, pa, sa, tb, Rb, pb, sb, m); }
+int hostsim_pair_f64(int ta, const double* Ra, const double* pa, const double* sa, int tb, const double* Rb, const double* pb, const double* sb, double m) { return pair_impl<double>(ta, Ra, pa, sa, tb, Rb, pb, sb, m); }
 int hostsim_fk_f32(const gik_table_t* t, int64_t n, const float* q, float* f) { return fk_impl<float>(t, n, q, f); }
 int hostsim_fk_f64(const gik_table_t* t, int64_t n, const double* q, double* f) { return fk_impl<double>(t, n, q, f); }
 int hostsim_jac_f32(const gik_table_t* t, int64_t n, const float* q, float* j) { return jac_impl<float>(t, n, q, j); }

@@ -1,0 +1,93 @@
+"""GPU collision kernels (through the C ABI) against the CPU oracle (alternating projections, oracle/collision_oracle.inc)
+on the same seeded inputs, plus the reference's known answers."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rot_rpy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver(table):
+    import gik_b200
+    s = gik_b200.GraspIK(table, "cuda:0").attach_scene()
+    yield s
+    s.close()
+
+
+def _t(a, dtype):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda:0")
+
+
+def _inputs(table, n, seed):
+    rng = np.random.default_rng(seed)
+    Q = rng.uniform(table.lower, table.upper, size=(n, 15)) * 0.7
+    Q[0] = 0.0
+    P = np.zeros((n, 12)); P[:, [0, 4, 8]] = 1
+    P[:, 9:] = rng.uniform([0.2, -0.4, 0.93], [0.6, 0.4, 1.4], size=(n, 3))
+    P[1::5, :9] = rot_rpy(0, 0, 0.5).reshape(9)
+    return Q, P
+
+
+@pytest.mark.parametrize("dtype,band", [(torch.float64, 1e-6), (torch.float32, 1e-4)])
+def test_collision_and_clearance_match_oracle(solver, table, table_c, scene_c, c_oracle, dtype, band):
+    n = 1203                                                       # not a multiple of the warps per block
+    Q, P = _inputs(table, n, 3)
+    d_all = c_oracle.scene_distance(table_c, scene_c, Q, P, mode=0, cull=0.05)
+    d_obs = c_oracle.scene_distance(table_c, scene_c, Q, P, mode=1, cull=0.2)
+    qs, ps = _t(Q, dtype).t().contiguous(), _t(P, dtype).t().contiguous()
+    col = solver.collision_soa(qs, ps).bool().cpu().numpy()
+    sure = (d_all == 0) | (d_all > band)
+    assert sure.mean() > 0.95 and (col[sure] == (d_all[sure] == 0)).all()
+    assert col[0]                                                  # collision(robot, q0) is True (lab_instructions.ipynb:252)
+    assert 0.05 < col.mean() < 0.98
+    clear = solver.clearance_soa(qs, ps, 0.04).bool().cpu().numpy()
+    sure = np.abs(d_obs - 0.04) > 10 * band
+    assert (clear[sure] == (d_obs[sure] >= 0.04)).all()
+    # row-major convenience + default cube placement of the scene
+    c2 = solver.collision(_t(Q[:64], dtype), _t(P[:64], dtype)).cpu().numpy()
+    assert (c2 == col[:64]).all()
+    d_def = c_oracle.scene_distance(table_c, scene_c, Q[:64], None, mode=0, cull=0.05)
+    c3 = solver.collision(_t(Q[:64], dtype)).cpu().numpy()
+    sure = (d_def == 0) | (d_def > band)
+    assert (c3[sure] == (d_def[sure] == 0)).all()
+
+
+def test_cube_collision_matches_oracle(solver, table_c, scene_c, c_oracle):
+    rng = np.random.default_rng(5)
+    n = 999
+    P = np.zeros((n, 12)); P[:, [0, 4, 8]] = 1
+    P[:, 9:] = rng.uniform([0.2, -0.3, 0.85], [0.65, 0.15, 1.1], size=(n, 3))
+    P[::3, :9] = rot_rpy(0.1, -0.2, 0.6).reshape(9)
+    dc = c_oracle.scene_distance(table_c, scene_c, None, P, mode=2)
+    for dtype, band in ((torch.float64, 1e-6), (torch.float32, 1e-4)):
+        got = solver.cube_collision_soa(_t(P, dtype).t().contiguous()).bool().cpu().numpy()
+        sure = (dc == 0) | (dc > band)
+        assert (got[sure] == (dc[sure] == 0)).all() and 0.1 < got.mean() < 0.9
+
+
+def test_golden_grasp_poses_are_collision_free(solver, golden):
+    Q = np.array([c["q"] for c in golden["cases"]])
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    for dtype in (torch.float64, torch.float32):
+        assert not solver.collision(_t(Q, dtype), _t(P, dtype)).any()      # the reference returned success=True for both
+    assert solver.collision(_t(Q, torch.float64)).any() is not None
+
+
+def test_collision_error_codes(table):
+    import ctypes
+    import gik_b200
+    from gik_b200 import _cabi
+    s = gik_b200.GraspIK(table, "cuda:0")
+    z = ctypes.c_void_p(0)
+    assert _cabi.lib().gik_collision_f32(s._h, 4, z, z, z, z) == -7           # GIK_E_NOSCENE
+    s.attach_scene()
+    assert _cabi.lib().gik_collision_f32(s._h, 4, z, z, z, z) == -1           # GIK_E_NULL
+    assert _cabi.lib().gik_collision_f32(s._h, 0, z, z, z, z) == 0
+    bad = gik_b200.nextage_scene()
+    bad.geoms[3].joint = 99
+    with pytest.raises(_cabi.GikError):
+        s.attach_scene(bad)
+    s.close()
