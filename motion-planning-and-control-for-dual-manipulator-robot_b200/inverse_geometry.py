@@ -11,9 +11,10 @@ What is preserved from the reference function
     configuration does not collide (:97-98).  While converged-but-colliding the reference keeps descending; that
     is reproduced by single-step re-entry of the kernel with the collision test in between.
   * never raises on non-convergence.
-`collision` is taken from (in this order) the `collision=` keyword, the reference's own `tools.collision` when
-pinocchio objects are passed and `tools` is importable, else None (success = converged; the caller applies its
-collision test -- stated in INTEGRATION.md).
+`collision` is taken from (in this order) the `collision=` keyword (a callable q -> bool, or None to skip the test),
+the reference's own pinocchio `computeCollisions` when pinocchio objects are passed, else the GPU collision kernel on
+the packaged reference scene (scene.nextage_scene(): same geometries, pairs and placements as setup_pinocchio.py
+builds) when the solver runs the built-in Nextage table.
 """
 from __future__ import annotations
 
@@ -110,9 +111,12 @@ def computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None, *, collision=
     (float64 by default so results match the reference at round-off level)."""
     solver = solver_for(robot, cube)
     _setcubeplacement(robot, cube, cubetarget)
+    pose = torch.from_numpy(_pose_to_array(cubetarget)).to(solver.device)
     if collision == "auto":
         collision = _reference_collision(robot)
-    pose = torch.from_numpy(_pose_to_array(cubetarget)).to(solver.device)
+        if collision is None and solver.table.meta.get("source") in ("builtin-nextage", "urdf", "pinocchio"):
+            solver._need_scene()
+            collision = lambda qq: bool(solver.collision(qq, pose)[0].item())     # GPU kernel, reference scene
     q0 = torch.as_tensor(np.asarray(qcurrent, dtype=np.float64).copy(), device=solver.device)
 
     q, conv, info = solver.solve(q0, pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
@@ -152,14 +156,34 @@ def computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None, *, collision=
 
 
 def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, eps=EPSILON, dt=DT,
-                            max_iters=MAX_ITERS, damping=0.0, restarts=1, generator=None, return_info=False):
+                            max_iters=MAX_ITERS, damping=0.0, restarts=1, generator=None, return_info=False,
+                            collision=False):
     """Batched entry point (new).  `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (Nextage).
     q_init [B,nq] or [nq]; cube_pose [B,12|4x4|7|3].  Returns torch CUDA tensors (q [B,nq], converged bool [B]
     [, SolveInfo]); no host synchronisation.  With restarts=R > 1, restart 0 starts from q_init and restarts
     1..R-1 from configurations drawn uniformly inside the joint limits; the best converged candidate (smallest
-    max residual, ties -> lowest restart) is returned (BASELINE config 3).  The collision term of the
-    reference's success predicate is NOT applied here: see `apply_collision`."""
+    max residual, ties -> lowest restart) is returned (BASELINE config 3).  `collision=True` makes the returned flag
+    the reference's full `success` (converged and collision-free on the attached scene, with the reference's
+    keep-descending-while-colliding behaviour: GraspIK.solve_success_soa); the default returns `converged` only (the
+    north_star's kernel contract; `apply_collision` applies a host-side test afterwards)."""
     solver = solver_for(robot)
+    if collision and restarts <= 1:
+        p12 = as_pose12(cube_pose, dtype=dtype, device=solver.device)
+        B = p12.shape[0]
+        qi = torch.as_tensor(q_init, device=solver.device).to(dtype)
+        if qi.dim() == 1:
+            qi = qi.unsqueeze(0).expand(B, solver.nq)
+        q, succ, conv, iters, resid = solver.solve_success_soa(qi.t().contiguous(), p12.t().contiguous(), eps=eps, dt=dt,
+                                                              max_iters=max_iters, damping=damping)
+        res = (q.t(), succ.bool())
+        if return_info:
+            from .ops import SolveInfo
+            info = SolveInfo(iters, resid.t())
+            info.converged = conv.bool()
+            res = res + (info,)
+        return res
+    if collision:
+        raise NotImplementedError("collision=True with restarts > 1: filter the candidates with GraspIK.collision_soa")
     if restarts <= 1:
         return solver.solve(q_init, cube_pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
                             return_info=return_info)

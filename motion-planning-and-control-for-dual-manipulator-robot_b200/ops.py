@@ -293,6 +293,45 @@ class GraspIK:
             cp = as_pose12(cube_pose, dtype=dtype, device=self.device, batch=qt.shape[0]).t().contiguous()
         return self.collision_soa(qt.t().contiguous(), cp).bool()
 
+    def solve_success_soa(self, q_init, pose, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0, kernel=None,
+                          descend_while_colliding=True):
+        """The reference's FULL success predicate on the device: `success = converged and not collision(q)`
+        (inverse_geometry.py:70, 97-98), including its behaviour on converged-but-colliding iterates -- the loop keeps
+        descending (the residual keeps shrinking) and re-tests after every update until the configuration is
+        collision-free or max_iters is reached.  One batched solve, one batched collision test, then single-update
+        re-entry rounds over the problems that are converged and colliding.  That tail is what the reference pays too
+        (one collision() per extra iteration); `descend_while_colliding=False` skips it: success is then
+        `converged and not collision(q at convergence)`, which differs from the reference only if further descent
+        would have freed the collision (and in the q returned for failed problems).
+        -> (q [nq][n], success u8 [n], converged u8 [n], iters i32 [n], resid [2][n])."""
+        self._need_scene()
+        q, conv, iters, resid = self.solve_soa(q_init, pose, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
+                                               kernel=kernel)
+        col = self.collision_soa(q, pose).bool()
+        convb = conv.bool()
+        success = convb & ~col
+        pending = torch.nonzero(convb & col & (iters < max_iters)).flatten()
+        if not descend_while_colliding:
+            pending = pending[:0]
+        tiny = float(np.finfo(np.float32 if q.dtype == torch.float32 else np.float64).tiny)
+        while pending.numel():                                  # host-visible loop: sizes shrink to zero quickly
+            qs = q[:, pending].contiguous()
+            ps = pose[:, pending].contiguous()
+            q1, _, _, r1 = self.solve_soa(qs, ps, eps=tiny, dt=dt, max_iters=1, damping=damping)    # exactly one update
+            it1 = iters[pending] + 1
+            ok = (r1[0] < eps) & (r1[1] < eps) & (it1 < max_iters)            # predicate evaluated at loop index it1
+            c1 = self.collision_soa(q1, ps).bool()
+            q[:, pending] = q1
+            iters[pending] = it1
+            resid[:, pending] = r1
+            conv[pending] = ok.to(torch.uint8)
+            good = ok & ~c1
+            success[pending] = good
+            pending = pending[~good & (it1 < max_iters)]
+        # the final test of inverse_geometry.py:97-98 re-evaluates collision(q) on the returned q: for a successful
+        # problem that is the configuration just found collision-free, for the others success is already False
+        return q, success.to(torch.uint8), conv, iters, resid
+
     # ------------------------------------------------------------------ row-major convenience ([B, ...])
     def fk(self, q: torch.Tensor):
         """q [B,nq] -> (R [B,2,3,3], p [B,2,3]) world placements of LARM_EFF / RARM_EFF."""

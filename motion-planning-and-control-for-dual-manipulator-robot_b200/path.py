@@ -30,21 +30,46 @@ def sample_cube_placements(n, p0, p1, *, z_range=(Z_MIN, Z_MAX), device="cuda", 
     return lo + u * (hi - lo)
 
 
+MIN_OBSTACLE_DISTANCE = 0.04      # path.py:32
+
+
 def sample_grasp_poses_batch(robot, n, cubeplacementq0, cubeplacementqgoal, *, q0=None, dtype=torch.float32,
-                             generator=None, cube_collision=None, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
+                             generator=None, cube_collision="scene", collision="scene",
+                             min_obstacle_distance=MIN_OBSTACLE_DISTANCE, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
                              damping=0.0):
-    """n candidate samples of path.sample_cube_placement evaluated at once: every placement gets one IK solve
-    from `q0` (robot.q0 = zeros by default, path.py:57).  Returns (q [n,nq], placements [n,3], ok bool [n]);
-    `ok` = IK converged (and `cube_collision(placements) -> bool [n]` is False when given)."""
+    """n candidate samples of path.sample_cube_placement (path.py:27-67) evaluated at once, every filter on the GPU:
+      1. placement uniform in the box of path.py:35-45, identity rotation (:47);
+      2. reject if the cube collides with the table / obstacle (:50-54)          -> gik_cube_collision_*
+      3. IK from `q0` (robot.q0 = zeros, :57) with the reference's success flag  -> gik_solve_* + gik_collision_*
+      4. reject if distanceToObstacle(robot, q) < min_obstacle_distance (:61-62) -> gik_clearance_*
+    Returns (q [n,nq], placements [n,3], ok bool [n]).  `cube_collision` / `collision`: "scene" = the attached
+    collision scene, None = skip that filter, or a callable (placements [n,3] -> bool [n]) / (q ndarray -> bool)."""
     solver = solver_for(robot)
     a = _pose_to_array(cubeplacementq0)
     b = _pose_to_array(cubeplacementqgoal)
     pl = sample_cube_placements(n, a[9:], b[9:], device=solver.device, dtype=dtype, generator=generator)
     qi = torch.zeros(solver.nq, dtype=dtype, device=solver.device) if q0 is None else torch.as_tensor(q0, device=solver.device).to(dtype)
-    q, conv = solver.solve(qi, pl, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
-    if cube_collision is not None:
-        conv = conv & ~torch.as_tensor(cube_collision(pl), device=solver.device).bool()
-    return q, pl, conv
+    p12 = as_pose12(pl, dtype=dtype, device=solver.device)
+    pose_soa = p12.t().contiguous()
+    if collision == "scene":
+        # a converged-but-colliding sample is rejected either way; the reference's extra descent on it is skipped
+        q_soa, succ, _, _, _ = solver.solve_success_soa(qi.unsqueeze(1).expand(solver.nq, n).contiguous(), pose_soa, eps=eps,
+                                                        dt=dt, max_iters=max_iters, damping=damping,
+                                                        descend_while_colliding=False)
+        ok = succ.bool()
+        if min_obstacle_distance is not None and min_obstacle_distance > 0:
+            ok &= solver.clearance_soa(q_soa, pose_soa, min_obstacle_distance).bool()
+        q = q_soa.t()
+    else:
+        q, ok = solver.solve(qi, pl, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
+        if callable(collision):
+            from .inverse_geometry import apply_collision
+            ok = apply_collision(q, ok, collision)
+    if cube_collision == "scene":
+        ok = ok & ~solver.cube_collision_soa(pose_soa).bool()
+    elif callable(cube_collision):
+        ok = ok & ~torch.as_tensor(cube_collision(pl), device=solver.device).bool()
+    return q, pl, ok
 
 
 def edge_num_steps(cube_a12: torch.Tensor, cube_b12: torch.Tensor, step_size=STEP_SIZE) -> torch.Tensor:

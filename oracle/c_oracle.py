@@ -109,6 +109,16 @@ def scene_distance(table_c, scene_c, q, cube_pose=None, mode=0, cull=0.0, thread
     return out
 
 
+def solve_success(table_c, scene_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0):
+    """computeqgrasppose with the collision term of the predicate (inverse_geometry.py:70, 97-98)."""
+    q_init = _c(q_init); pose12 = _c(pose12); n, nq = q_init.shape
+    q = np.empty((n, nq)); ok = np.empty(n, np.uint8); it = np.empty(n, np.int32)
+    lib().orc_solve_success(ctypes.byref(table_c), ctypes.byref(scene_c), ctypes.c_int64(n), _p(q_init), _p(pose12),
+                            ctypes.c_double(eps), ctypes.c_double(dt), ctypes.c_int(max_iters), ctypes.c_int(threads),
+                            _p(q), _p(ok), _p(it))
+    return q, ok.astype(bool), it
+
+
 def pair_distance(type_a, Ra, pa, sa, type_b, Rb, pb, sb):
     L = lib()
     L.orc_pair_distance.restype = ctypes.c_double

@@ -91,3 +91,49 @@ def test_collision_error_codes(table):
     with pytest.raises(_cabi.GikError):
         s.attach_scene(bad)
     s.close()
+
+
+def test_full_success_predicate_matches_oracle(solver, table_c, scene_c, c_oracle):
+    # computeqgrasppose WITH the collision term (inverse_geometry.py:70, 97-98), including the reference's
+    # keep-descending-while-colliding tail: same success flags, same iteration counts, same q
+    from conftest import make_poses
+    import gik_b200
+    n = 96
+    P = make_poses(n, 77)
+    qo, oko, ito = c_oracle.solve_success(table_c, scene_c, np.zeros((n, 15)), P)
+    q, ok, info = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), _t(P, torch.float64), dtype=torch.float64,
+                                                   collision=True, return_info=True)
+    ok = ok.cpu().numpy(); q = q.cpu().numpy(); it = info.iters.cpu().numpy()
+    assert (ok == oko).all()
+    assert (it == ito).mean() >= 0.98
+    d = np.abs(q - qo).max(axis=1)
+    assert np.quantile(d[ok], 0.95) < 1e-9 and np.quantile(d, 0.9) < 1e-6
+    _, conv = solver.solve(torch.zeros(15), _t(P, torch.float64), dtype=torch.float64)
+    conv = conv.cpu().numpy()
+    assert (conv & ~ok).sum() >= 5                     # the batch does contain converged-but-colliding problems
+    assert (it[conv & ~ok] == 1000).all()              # ... which kept descending to the iteration cap, like the reference
+    # skipping the extra descent gives the same decisions on this batch
+    q2, s2, c2, it2, _ = solver.solve_success_soa(torch.zeros((15, n), dtype=torch.float64, device="cuda:0"),
+                                                  _t(P, torch.float64).t().contiguous(), descend_while_colliding=False)
+    assert (s2.bool().cpu().numpy() == oko).all()
+    # single-call drop-in: full reference semantics without pinocchio (GPU collision on the packaged scene)
+    i_bad = int(np.nonzero(conv & ~ok)[0][0]); i_good = int(np.nonzero(ok)[0][0])
+    for i in (i_bad, i_good):
+        qs, ss = gik_b200.computeqgrasppose(None, np.zeros(15), None, (np.eye(3), P[i, 9:]))
+        assert ss == bool(oko[i]) and np.abs(qs - qo[i]).max() < 1e-6
+
+
+def test_batched_sampler_applies_every_reference_filter(solver, table_c, scene_c, c_oracle):
+    import gik_b200
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    a = (np.eye(3), np.array([0.33, -0.3, 0.93])); b = (np.eye(3), np.array([0.4, 0.11, 0.93]))   # config.py:36-37
+    q, pl, ok = gik_b200.sample_grasp_poses_batch(solver, 2048, a, b, dtype=torch.float64, generator=g)
+    pl_np = pl.cpu().numpy(); okn = ok.cpu().numpy(); qn = q.cpu().numpy()
+    assert 0.02 < okn.mean() < 0.6
+    assert (pl_np[:, 0] >= 0.33).all() and (pl_np[:, 0] <= 0.4).all() and (pl_np[:, 2] >= 1.05).all() and (pl_np[:, 2] <= 1.4).all()
+    P = np.zeros((len(pl_np), 12)); P[:, [0, 4, 8]] = 1; P[:, 9:] = pl_np
+    idx = np.nonzero(okn)[0][:40]
+    # accepted samples satisfy every predicate of path.sample_cube_placement according to the oracle
+    assert (c_oracle.scene_distance(table_c, scene_c, None, P[idx], mode=2) > 0).all()             # path.py:51-54
+    assert (c_oracle.scene_distance(table_c, scene_c, qn[idx], P[idx], mode=0, cull=0.05) > 0).all()  # :57-59
+    assert (c_oracle.scene_distance(table_c, scene_c, qn[idx], P[idx], mode=1, cull=0.2) >= 0.04 - 1e-6).all()   # :61-62
