@@ -10,7 +10,7 @@ from .scene import CollisionScene, nextage_scene, scene_from_urdf               
 from .ops import (DT, EPSILON, MAX_ITERS, GraspIK, SolveInfo, as_pose12, bytes_per_solve,  # noqa: F401
                   default_solver, flops_per_iter, fma_peak_tflops)
 from .inverse_geometry import apply_collision, computeqgrasppose, computeqgrasppose_batch, solver_for  # noqa: F401
-from .path import (edge_num_steps, project_edges_batch, project_path, sample_cube_placements,  # noqa: F401
+from .path import (computepath, edge_num_steps, project_edges_batch, project_path, sample_cube_placements,  # noqa: F401
                    sample_grasp_poses_batch, se3_interpolate)
 from . import dist                                                                     # noqa: F401
 from ._cabi import GikError, build                                                     # noqa: F401

@@ -307,8 +307,13 @@ class GraspIK:
         self._need_scene()
         q, conv, iters, resid = self.solve_soa(q_init, pose, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
                                                kernel=kernel)
-        col = self.collision_soa(q, pose).bool()
         convb = conv.bool()
+        # the predicate short-circuits (inverse_geometry.py:70): collision() is only evaluated where both residuals
+        # pass, so only the converged columns are tested
+        idx = torch.nonzero(convb).flatten()
+        col = torch.zeros_like(convb)
+        if idx.numel():
+            col[idx] = self.collision_soa(q[:, idx].contiguous(), pose[:, idx].contiguous()).bool()
         success = convb & ~col
         pending = torch.nonzero(convb & col & (iters < max_iters)).flatten()
         if not descend_while_colliding:

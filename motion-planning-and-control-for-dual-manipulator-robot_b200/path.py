@@ -113,8 +113,12 @@ def project_edges_batch(robot, q_start, cube_a, cube_b, *, num_steps=None, step_
 def project_path(robot, cube, q_curr, cube_curr, cube_rand, step_size=STEP_SIZE, viz=None, *, cube_collision=None,
                  collision=None, dtype=torch.float64):
     """Drop-in for path.project_path (path.py:125-163), one edge: returns (robot_path, cube_path), both starting
-    with the given q / placement.  `cube_collision(pose12) -> bool` and `collision(q) -> bool` reproduce the
-    host-side tests of path.py:144-149 and inverse_geometry.py:70 when given."""
+    with the given q / placement.  The march itself (SE3.Interpolate, warm-started IK, stop at the first non-converged
+    step) is ONE launch of the edge kernel; the two collision tests of the reference loop -- the cube against the
+    table / obstacle (path.py:144-149) and the robot (the collision term of computeqgrasppose's predicate) -- are then
+    applied to all steps at once and the path is cut at the first step that fails either.
+    `cube_collision` / `collision`: None = no test, "scene" = the GPU kernels on the attached scene, or host callables
+    (pose12 -> bool) / (q -> bool)."""
     solver = solver_for(robot, cube)
     a = _pose_to_array(cube_curr)
     b = _pose_to_array(cube_rand)
@@ -124,18 +128,122 @@ def project_path(robot, cube, q_curr, cube_curr, cube_rand, step_size=STEP_SIZE,
     n_ok = int(nv[0].item())
     qs = q_path[0].double().cpu().numpy()
     robot_path, cube_path = [q_curr], [cube_curr]
+    if n_ok == 0:
+        return robot_path, cube_path
     # placements along the edge, same interpolation as the kernel, for the returned cube_path
-    A = torch.from_numpy(a)[None]
-    B = torch.from_numpy(b)[None]
+    A = torch.from_numpy(a)[None].expand(n_ok, 12)
+    B = torch.from_numpy(b)[None].expand(n_ok, 12)
+    alphas = [(k + 1) / num_steps for k in range(n_ok)]
+    poses = torch.cat([se3_interpolate(A[k:k + 1], B[k:k + 1], alphas[k]) for k in range(n_ok)], 0)
+    bad = np.zeros(n_ok, bool)
+    if cube_collision == "scene" or collision == "scene":
+        pd = poses.to(solver.device, dtype).t().contiguous()
+        if cube_collision == "scene":
+            bad |= solver.cube_collision_soa(pd).bool().cpu().numpy()
+        if collision == "scene":
+            qd = q_path[0, :n_ok].to(dtype).t().contiguous()
+            bad |= solver.collision_soa(qd, pd).bool().cpu().numpy()
+    poses = poses.numpy()
     for k in range(n_ok):
-        pose = se3_interpolate(A, B, (k + 1) / num_steps)[0].numpy()
-        if cube_collision is not None and cube_collision(pose):
-            break
-        if collision is not None and collision(qs[k]):
+        if bad[k] or (callable(cube_collision) and cube_collision(poses[k])) or (callable(collision) and collision(qs[k])):
             break
         robot_path.append(qs[k].copy())
-        cube_path.append(_like(cube_curr, pose))
+        cube_path.append(_like(cube_curr, poses[k]))
     return robot_path, cube_path
+
+
+# ------------------------------------------------------------------------------------------------------
+# RRT-connect driver (path.computepath, path.py:194-278): the reference's tree logic, with its two IK call sites
+# replaced by the batched sampler (a pool of pre-validated samples) and the edge kernel.
+# ------------------------------------------------------------------------------------------------------
+GOAL_TOLERANCE = 0.5        # path.py:202
+GOAL_BIAS = 0.1             # path.py:224
+MAX_ITERATIONS = 250        # path.py:199
+MAX_RETRIES = 10            # path.py:200
+
+
+class _SamplePool:
+    """Stream of valid (q, placement) samples of path.sample_cube_placement, drawn `batch` candidates at a time on the
+    GPU.  Taking the next valid sample of an i.i.d. candidate stream is what the reference's rejection loop does."""
+
+    def __init__(self, solver, a, b, dtype, batch, generator, scene):
+        self.args = (solver, a, b, dtype, batch, generator, scene)
+        self.q, self.pl = [], []
+
+    def next(self):
+        solver, a, b, dtype, batch, generator, scene = self.args
+        while not self.q:
+            q, pl, ok = sample_grasp_poses_batch(solver, batch, a, b, dtype=dtype, generator=generator,
+                                                 cube_collision="scene" if scene else None,
+                                                 collision="scene" if scene else None)
+            idx = torch.nonzero(ok).flatten()
+            self.q = list(q[idx].double().cpu().numpy())
+            self.pl = list(pl[idx].double().cpu().numpy())
+        return self.q.pop(0), self.pl.pop(0)
+
+
+def _get_path(G):
+    """path.get_path (path.py:174-183)."""
+    path, node = [], G[-1]
+    while node[0] is not None:
+        path.insert(0, node[1])
+        node = G[node[0]]
+    path.insert(0, G[0][1])
+    return path
+
+
+def computepath(qinit, qgoal, cubeplacementq0, cubeplacementqgoal, robot=None, cube=None, *, step_size=STEP_SIZE,
+                goal_tolerance=GOAL_TOLERANCE, max_iterations=MAX_ITERATIONS, max_retries=MAX_RETRIES, rng=None,
+                generator=None, dtype=torch.float64, sample_batch=512, scene=True, return_stats=False):
+    """Drop-in for path.computepath (path.py:194-278): bidirectional RRT over cube placements, each new vertex a grasp
+    configuration.  Same loop as the reference (goal bias 0.1, nearest vertex in configuration space, project_path
+    towards the sample from the start tree and towards the goal placement from the goal tree, connect when the two new
+    configurations are closer than goal_tolerance); the IK, interpolation and collision work runs in the CUDA kernels.
+    `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (built-in Nextage); `cube` is unused unless
+    `robot` is a pinocchio wrapper.  Returns the list of configurations (empty on failure), like the reference."""
+    solver = solver_for(robot, cube)
+    if scene:
+        solver._need_scene()
+    rng = rng if rng is not None else np.random.default_rng()
+    qinit, qgoal = np.asarray(qinit, float), np.asarray(qgoal, float)
+    a12, b12 = _pose_to_array(cubeplacementq0), _pose_to_array(cubeplacementqgoal)
+    pool = _SamplePool(solver, a12, b12, dtype, sample_batch, generator, scene)
+    test = "scene" if scene else None
+    stats = {"iterations": 0, "retries": 0, "edges": 0, "vertices": 0}
+
+    def nearest(points, target):            # KDTree.query of the reference (path.py:186-192): exact nearest neighbour
+        return int(np.argmin(((np.asarray(points) - target) ** 2).sum(axis=1)))
+
+    for retry in range(max_retries):
+        G_start, G_goal = [(None, qinit)], [(None, qgoal)]
+        C_start, C_goal = [a12], [b12]
+        for i in range(max_iterations):
+            stats["iterations"] += 1
+            if rng.random() < GOAL_BIAS:
+                q_rand, cube_rand = qgoal, b12
+            else:
+                q_rand, p = pool.next()
+                cube_rand = np.concatenate([np.eye(3).reshape(9), p])
+            ns = nearest([g[1] for g in G_start], q_rand)
+            seg_q, seg_c = project_path(solver, None, G_start[ns][1], C_start[ns], cube_rand, step_size=step_size,
+                                        cube_collision=test, collision=test, dtype=dtype)
+            for j in range(len(seg_q)):     # the reference re-adds the segment's first vertex too (path.py:241-244)
+                G_start.append((len(G_start) - 1 if j > 0 else ns, seg_q[j]))
+                C_start.append(_pose_to_array(seg_c[j]))
+            q_new = seg_q[-1]
+            ng = nearest([g[1] for g in G_goal], q_new)
+            seg_q2, seg_c2 = project_path(solver, None, G_goal[ng][1], C_goal[ng], b12, step_size=step_size,
+                                          cube_collision=test, collision=test, dtype=dtype)
+            for j in range(len(seg_q2)):
+                G_goal.append((len(G_goal) - 1 if j > 0 else ng, seg_q2[j]))
+                C_goal.append(_pose_to_array(seg_c2[j]))
+            stats["edges"] += 2
+            if np.linalg.norm(seg_q2[-1] - q_new) < goal_tolerance:
+                path = _get_path(G_start) + _get_path(G_goal)[::-1]
+                stats["vertices"] = len(G_start) + len(G_goal)
+                return (path, stats) if return_stats else path
+        stats["retries"] += 1
+    return ([], stats) if return_stats else []
 
 
 def _like(template, pose12):

@@ -137,3 +137,29 @@ def test_batched_sampler_applies_every_reference_filter(solver, table_c, scene_c
     assert (c_oracle.scene_distance(table_c, scene_c, None, P[idx], mode=2) > 0).all()             # path.py:51-54
     assert (c_oracle.scene_distance(table_c, scene_c, qn[idx], P[idx], mode=0, cull=0.05) > 0).all()  # :57-59
     assert (c_oracle.scene_distance(table_c, scene_c, qn[idx], P[idx], mode=1, cull=0.2) >= 0.04 - 1e-6).all()   # :61-62
+
+
+def test_rrt_connect_driver_end_to_end(solver, table, table_c, scene_c, c_oracle, golden):
+    # path.computepath (path.py:194-278) on the reference's own query: carry the cube from CUBE_PLACEMENT to
+    # CUBE_PLACEMENT_TARGET over the obstacle, starting and ending at the recorded grasp poses
+    import time
+    import gik_b200
+    q0 = np.array(golden["cases"][0]["q"]); qe = np.array(golden["cases"][1]["q"])
+    a = (np.eye(3), np.array(golden["cases"][0]["cube_p"])); b = (np.eye(3), np.array(golden["cases"][1]["cube_p"]))
+    t0 = time.perf_counter()
+    path, stats = gik_b200.computepath(q0, qe, a, b, robot=solver, rng=np.random.default_rng(0),
+                                       generator=torch.Generator(device="cuda:0").manual_seed(0), return_stats=True)
+    dt = time.perf_counter() - t0
+    print(f"computepath: {len(path)} configurations, {stats}, {dt:.2f} s")
+    assert len(path) >= 3 and np.array_equal(path[0], q0) and np.array_equal(path[-1], qe)
+    Q = np.array(path)
+    assert (Q >= table.lower - 1e-9).all() and (Q <= table.upper + 1e-9).all()
+    # every vertex still holds the cube: the two hand frames are one cube width apart (hooks at +-0.05, cube_small.urdf:34-48)
+    R, p = c_oracle.fk(table_c, Q)
+    assert np.abs(np.linalg.norm(p[:, 0] - p[:, 1], axis=1) - 0.1).max() < 3e-3
+    # ... and stays clear of the table and the obstacle (robot geometries; oracle distances)
+    assert (c_oracle.scene_distance(table_c, scene_c, Q, None, mode=1, cull=0.3) > 0).all()
+    # consecutive vertices inside a segment move the cube by at most one step (0.025 m): hands move accordingly
+    mid = 0.5 * (p[:, 0] + p[:, 1])
+    jumps = np.linalg.norm(np.diff(mid, axis=0), axis=1)
+    assert np.quantile(jumps, 0.9) < 0.03
