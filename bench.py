@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: 'fused' = the solve kernel stores results into every rank's symmetric-memory arrays over "
                          "NVLink (falls back to nccl if symmetric memory is unavailable); 'nccl' = all_gather_into_tensor")
-    ap.add_argument("--kernel", default=None, choices=["lane", "pair"], help="force a thread mapping (default: launcher's choice)")
+    ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = "f64" if args.config == 3 else "f32"

@@ -79,6 +79,7 @@ typedef struct gik_params_s {
  * per lane) below that.  These force one mapping (A/B measurements, tests). */
 #define GIK_F_LANE_KERNEL 2
 #define GIK_F_PAIR_KERNEL 4
+#define GIK_F_SCALAR_LANE 8   /* fp32 lane mapping with scalar FFMA instead of the packed FFMA2 kernel (A/B only) */
 
 typedef struct gik_handle_s* gik_handle_t;
 

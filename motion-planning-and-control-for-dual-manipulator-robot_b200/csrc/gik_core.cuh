@@ -166,6 +166,62 @@ GIK_HD float atan2_pos(float y, float x) {
 }
 GIK_HD double atan2_pos(double y, double x) { return atan2(y, x); }
 
+// ------------------------------------------------------------------------------------------------------
+// F2: two fp32 values in one 64-bit register pair, operated on by Blackwell's packed FFMA2 / FMUL2 / FADD2
+// (PTX fma/mul/add/sub.rn.f32x2, sm_100+).  One packed instruction does the work of two scalar ones in ONE issue slot
+// (measured on B200, tools/probes/ffma2.cu: 68.4 TFLOP/s with three register operands, where scalar FFMA with three
+// register operands stops at 45 TFLOP/s on register-file bandwidth).  The two hands of one problem run the same
+// operation sequence on different data, so the fp32 lane kernel carries (left, right) in the halves of an F2.
+// ptxas contracts mul.f32x2 + add/sub.f32x2 into FFMA2 and folds negations into operand modifiers, so the templates
+// below are instantiated with T = F2 unchanged.  On the host (unit tests) the halves are plain floats.
+// ------------------------------------------------------------------------------------------------------
+struct F2 {
+  float x, y;
+  GIK_HD F2() {}
+  GIK_HD F2(float a) : x(a), y(a) {}
+  GIK_HD F2(double a) : x((float)a), y((float)a) {}
+  GIK_HD F2(int a) : x((float)a), y((float)a) {}
+  GIK_HD F2(float a, float b) : x(a), y(b) {}
+};
+#ifdef __CUDA_ARCH__
+GIK_HD unsigned long long f2_pack(F2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+GIK_HD F2 f2_unpack(unsigned long long r) {
+  F2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+GIK_HD F2 operator*(F2 a, F2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+GIK_HD F2 operator+(F2 a, F2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+GIK_HD F2 operator-(F2 a, F2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+#else
+GIK_HD F2 operator*(F2 a, F2 b) { return F2(a.x * b.x, a.y * b.y); }
+GIK_HD F2 operator+(F2 a, F2 b) { return F2(a.x + b.x, a.y + b.y); }
+GIK_HD F2 operator-(F2 a, F2 b) { return F2(a.x - b.x, a.y - b.y); }
+#endif
+GIK_HD F2 operator-(F2 a) { return F2(-a.x, -a.y); }
+GIK_HD F2& operator+=(F2& a, F2 b) { a = a + b; return a; }
+GIK_HD F2& operator-=(F2& a, F2 b) { a = a - b; return a; }
+GIK_HD F2 max_(F2 a, F2 b) { return F2(max_(a.x, b.x), max_(a.y, b.y)); }
+GIK_HD F2 min_(F2 a, F2 b) { return F2(min_(a.x, b.x), min_(a.y, b.y)); }
+GIK_HD F2 rsqrt_(F2 a) { return F2(rsqrt_(a.x), rsqrt_(a.y)); }
+template <> struct Num<F2> { static constexpr float kPivotFloor = 1e-30f; };
+
 // FAST = MUFU-based sin/cos (abs error ~5e-7 on [-pi, pi]); accurate otherwise.
 template <bool FAST>
 GIK_HD void sincos_(float x, float& s, float& c) {
@@ -300,6 +356,27 @@ GIK_HD void hand_error(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], T (
   log6(R, p, e);
 }
 
+// both hands at once: the products are packed, log6 (branches, transcendental functions) runs per half
+GIK_HD void hand_error(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], F2 (&e)[6]) {
+  F2 R[9], p[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      R[3 * r + c] = B[3 * r] * tgt[c] + B[3 * r + 1] * tgt[3 + c] + B[3 * r + 2] * tgt[6 + c];
+    p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
+  }
+  float Rl[9], Rr[9], pl[3], pr[3], el[6], er[6];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { Rl[i] = R[i].x; Rr[i] = R[i].y; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { pl[i] = p[i].x; pr[i] = p[i].y; }
+  log6(Rl, pl, el);
+  log6(Rr, pr, er);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) e[i] = F2(el[i], er[i]);
+}
+
 // One hand's share of the damped least-squares step.  Returns u = A^T G^-1 e, w = A^T G^-1 c over the six
 // arm joints (G = A A^T + lambda I, A = arm block, c = chest column) and this hand's c.G^-1 e, c.G^-1 c.
 template <typename T, int OFF, uint32_t TZ>
@@ -385,6 +462,41 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
     dq[1 + k] = uL[k] - kappa * wL[k];
     dq[7 + k] = uR[k] - kappa * wR[k];
   }
+}
+
+// fp32 lane kernel: the same iteration with (left, right) packed.  State: chest angle q0, arm angles q2[k] =
+// (q_L[k], q_R[k]), targets tgt2 = (left hook target, right hook target).  Returns the squared residuals and applies
+// nothing: the caller updates q0 with dq0 and q2 with dq2.
+struct PackedTable {
+  ArmConst<F2> arm;        // (left, right) constants of the two chains
+  F2 lo[6], hi[6];         // arm joint limits
+  float lo0, hi0;          // chest limits
+};
+
+template <uint32_t TZ>
+GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[6], const F2 (&tgt2)[12], float lambda,
+                                float& dq0, F2 (&dq2)[6], float& resid2L, float& resid2R) {
+  F2 cs[kActive], sn[kActive];      // only chain slots 0..6 are used
+  {
+    float s, c;
+    sincos_<true>(q0, s, c);
+    cs[0] = F2(c); sn[0] = F2(s);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float sl, cl, sr, cr;
+    sincos_<true>(q2[k].x, sl, cl);
+    sincos_<true>(q2[k].y, sr, cr);
+    cs[1 + k] = F2(cl, cr); sn[1 + k] = F2(sl, sr);
+  }
+  F2 u[6], w[6], Sy, Sz, r2;
+  hand_pass<F2, 0, TZ>(pt.arm, cs, sn, tgt2, F2(lambda), u, w, Sy, Sz, r2);
+  const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
+  dq0 = kappa;
+  const F2 nk = F2(-kappa);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dq2[k] = u[k] + nk * w[k];
+  resid2L = r2.x; resid2R = r2.y;
 }
 
 // q <- clamp(q + dt dq)  (pin.integrate on an all-revolute model :86, projecttojointlimits :89)

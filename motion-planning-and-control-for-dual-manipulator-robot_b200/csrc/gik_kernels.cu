@@ -200,6 +200,166 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
 
 
 // ========================================================================================================
+// fp32 lane kernel, packed: one problem per lane with the two hands carried in the halves of F2 registers, so the
+// chain walks, Gram matrices, Cholesky factorisations and solves of both hands issue as FFMA2 / FMUL2 / FADD2 --
+// half the issue slots of the scalar lane kernel for the same arithmetic (gik_core.cuh "F2").  Scheduling (global
+// work queue, lane refill) is the scalar lane kernel's.
+// ========================================================================================================
+#ifndef GIK_MINB_LANE2
+#define GIK_MINB_LANE2 3
+#endif
+template <int MODE, uint32_t TZ>
+__global__ void __launch_bounds__(GIK_THREADS, GIK_MINB_LANE2)
+gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid_constant__ PackedTable pt,
+                       const __grid_constant__ SolveArgs<float> a) {
+  using T = float;
+  const int lane = threadIdx.x & 31;
+  const int64_t n = a.n;
+  const int L = a.lanes;
+  const bool enabled = lane < L;
+
+  T q0 = T(0);
+  F2 q2[6], tgt2[12];          // (left, right) arm angles and hook targets
+#pragma unroll
+  for (int k = 0; k < 6; ++k) q2[k] = F2(0.0f);
+#pragma unroll
+  for (int c = 0; c < 12; ++c) tgt2[c] = F2((c % 4 == 0 && c < 9) ? 1.0f : 0.0f);
+  auto set_targets = [&](const T (&cube)[12]) {
+    T tl[12], tr[12];
+    hook_target(tab.arm[0], cube, tl);
+    hook_target(tab.arm[1], cube, tr);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) tgt2[c] = F2(tl[c], tr[c]);
+  };
+  auto store_q = [&](T* dst, int64_t ld, int64_t col) {
+    dst[(int64_t)tab.act_q[0] * ld + col] = q0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      dst[(int64_t)tab.act_q[1 + k] * ld + col] = q2[k].x;
+      dst[(int64_t)tab.act_q[7 + k] * ld + col] = q2[k].y;
+    }
+  };
+
+  int64_t idx = -1;     // problem (or edge) this lane works on
+  bool active = false;
+  bool exhausted = false;   // warp-uniform: the queue has handed out every problem
+  int it = 0;
+  // edge mode state
+  int step = 0, nsteps = 0, it_total = 0;
+
+  for (;;) {
+    // ---------------- refill: lanes without work pull the next problems from the global queue ----------------
+    // One atomicAdd per warp per refill (leader lane, count = lanes in need), so problems are handed out in index
+    // order to whichever lane frees up first: the tail of the launch is bounded by ONE problem's duration instead
+    // of by the slowest statically assigned lane.  The first refill of a warp takes 32 consecutive problems
+    // (coalesced loads).  A problem's arithmetic does not depend on the lane it lands on: results are bit-identical.
+    const unsigned need = exhausted ? 0u : __ballot_sync(0xffffffffu, enabled && !active);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
+      if (enabled && !active) {
+        const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+        if (cand < n) {
+          idx = cand;
+          active = true;
+          it = 0;
+          q0 = __ldg(a.q_init + (int64_t)tab.act_q[0] * n + idx);
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            q2[k] = F2(__ldg(a.q_init + (int64_t)tab.act_q[1 + k] * n + idx), __ldg(a.q_init + (int64_t)tab.act_q[7 + k] * n + idx));
+          T cube[12];
+          load_cube(a.pose, n, idx, cube);
+          if (MODE == MODE_EDGES) {
+            nsteps = __ldg(a.num_steps + idx);
+            step = 1;
+            it_total = 0;
+            T cb[12], xi[6], ca[12];
+#pragma unroll
+            for (int c = 0; c < 12; ++c) ca[c] = cube[c];
+            load_cube(a.pose_b, n, idx, cb);
+            se3_delta(ca, cb, xi);
+            se3_advance(ca, xi, T(1) / T(nsteps), cube);
+            if (nsteps < 1) {  // nothing to march: reference loop body never runs (path.py:137)
+              a.n_valid[idx] = 0;
+              if (a.iters) a.iters[idx] = 0;
+              active = false;
+            }
+          }
+          set_targets(cube);
+        }
+      }
+    }
+    if (exhausted && !__any_sync(0xffffffffu, active)) break;
+
+    // ---------------- one descent iteration for every lane ----------------
+    T dq0, rL, rR;
+    F2 dq2[6];
+    ik_iteration_packed<TZ>(pt, q0, q2, tgt2, a.lambda, dq0, dq2, rL, rR);
+    const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
+    const bool done = ok || (it >= a.max_iters);
+
+    if (!done) {
+      q0 = min_(max_(pt.lo0, q0 + a.dt * dq0), pt.hi0);
+      const F2 dt2 = F2(a.dt);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) q2[k] = min_(max_(pt.lo[k], q2[k] + dt2 * dq2[k]), pt.hi[k]);
+      ++it;
+    } else if (active) {
+      // ---------------- rare path: this lane's problem ended ----------------
+      if (MODE == MODE_BATCH) {
+        const int64_t col = a.out_off + idx;
+        for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
+          T* qo = a.q_dst[d];
+          store_q(qo, a.out_n, col);
+          for (int p = 0; p < tab.n_passive; ++p) {
+            const int j = tab.passive_q[p];
+            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
+            qo[(int64_t)j * a.out_n + col] = v;
+          }
+          a.conv_dst[d][col] = ok ? 1 : 0;
+        }
+        if (a.iters) a.iters[idx] = it;
+        if (a.resid) { a.resid[idx] = sqrt_(rL); a.resid[n + idx] = sqrt_(rR); }
+        active = false;
+      } else {
+        it_total += it;
+        if (ok) {
+          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n;
+          store_q(dst, n, idx);
+          for (int p = 0; p < tab.n_passive; ++p) {
+            const int j = tab.passive_q[p];
+            // passive joints: clamped once any update has been applied on this edge
+            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
+            dst[(int64_t)j * n + idx] = v;
+          }
+        }
+        if (ok && step < nsteps) {
+          ++step;
+          it = 0;
+          T ca[12], cb[12], xi[6], cube[12];
+          load_cube(a.pose, n, idx, ca);
+          load_cube(a.pose_b, n, idx, cb);
+          se3_delta(ca, cb, xi);
+          se3_advance(ca, xi, T(step) / T(nsteps), cube);
+          set_targets(cube);
+        } else {
+          a.n_valid[idx] = ok ? step : step - 1;
+          if (a.iters) a.iters[idx] = it_total;
+          active = false;
+        }
+      }
+    }
+  }
+}
+
+
+
+// ========================================================================================================
 // Pair kernel: ONE PROBLEM PER LANE PAIR (even lane = left hand, odd lane = right hand).  Each lane walks its
 // own hand's chain, factors its own 6x6 block and solves its two right-hand sides; the pair meets in three
 // warp shuffles per iteration (the two Sherman-Morrison scalars and the residual).  Per-warp instruction count per
@@ -445,6 +605,7 @@ struct gik_handle_s {
   int sm_count;
   gik_table_t host;
   DevTable<float> tab32;
+  PackedTable pt32;                  // (left, right)-packed constants of tab32 for the fp32 packed lane kernel
   DevTable<double> tab64;
   struct gik_scene_dev* scene;       // collision scene (gik_scene_attach), or null
   unsigned long long* queues;        // device: kQueueSlots work-queue heads, one per launch in flight
@@ -474,7 +635,7 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
   if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
-      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) != 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE)) != 0 ||
       (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
@@ -520,7 +681,13 @@ int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* b
 template <typename T, int MODE>
 int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair) {
   int64_t max_warps = 0;
-  int rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+  int rc;
+  if constexpr (sizeof(T) == 4) {
+    rc = (flags & GIK_F_SCALAR_LANE) ? grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps)
+                                     : grid_dims(h, gik_solve_lane2_kernel<MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+  } else {
+    rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+  }
   if (rc) return rc;
   *pair = sizeof(T) == 8 || n <= 16 * max_warps;
   if (flags & GIK_F_LANE_KERNEL) *pair = false;
@@ -551,6 +718,14 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   if (pair) {
     if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+  } else if constexpr (sizeof(T) == 4) {
+    if (prm->flags & GIK_F_SCALAR_LANE) {
+      if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      else gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    } else {                                             // packed FFMA2 lane kernel (default for fp32)
+      if (nx) gik_solve_lane2_kernel<MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
+      else gik_solve_lane2_kernel<MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
+    }
   } else {
     if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     else gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
@@ -689,6 +864,7 @@ int gik_create(const gik_table_t* host_table, int device, gik_handle_t* out) {
   h->host = *host_table;
   int rc = build_dev_table<float>(*host_table, h->tab32);
   if (rc == GIK_OK) rc = build_dev_table<double>(*host_table, h->tab64);
+  if (rc == GIK_OK) build_packed_table(h->tab32, h->pt32);
   if (rc != GIK_OK) { delete h; return rc; }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);

@@ -116,6 +116,21 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
   return GIK_OK;
 }
 
+// (left, right)-packed constants for the fp32 packed lane kernel
+inline void build_packed_table(const DevTable<float>& d, PackedTable& p) {
+  const ArmConst<float>&L = d.arm[0], &R = d.arm[1];
+  for (int k = 0; k < 7; ++k)
+    for (int i = 0; i < 3; ++i) p.arm.t[k][i] = F2(L.t[k][i], R.t[k][i]);
+  for (int i = 0; i < 9; ++i) { p.arm.finv_R[i] = F2(L.finv_R[i], R.finv_R[i]); p.arm.hook_R[i] = F2(L.hook_R[i], R.hook_R[i]); }
+  for (int i = 0; i < 3; ++i) {
+    p.arm.finv_p[i] = F2(L.finv_p[i], R.finv_p[i]);
+    p.arm.tip_lin[i] = F2(L.tip_lin[i], R.tip_lin[i]);
+    p.arm.hook_p[i] = F2(L.hook_p[i], R.hook_p[i]);
+  }
+  for (int k = 0; k < 6; ++k) { p.lo[k] = F2(d.lo[1 + k], d.lo[7 + k]); p.hi[k] = F2(d.hi[1 + k], d.hi[7 + k]); }
+  p.lo0 = d.lo[0]; p.hi0 = d.hi[0];
+}
+
 // ---- collision scene (gik_scene_t -> DevScene<T>) ----
 inline int validate_scene(const gik_table_t& t, const gik_scene_t& s) {
   if (s.n_geoms < 1 || s.n_geoms > GIK_MAX_GEOMS || s.n_pairs < 0 || s.n_pairs > GIK_MAX_PAIRS) return GIK_E_SIZE;

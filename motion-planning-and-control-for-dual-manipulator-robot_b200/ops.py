@@ -94,7 +94,8 @@ class GraspIK:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4}     # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL
+    # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL / GIK_F_SCALAR_LANE (fp32: "lane" = packed FFMA2 kernel, "lane1" = scalar)
+    _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4, "lane1": 2 | 8}
 
     def _params(self, eps, dt, max_iters, damping, kernel=None) -> _cabi.GikParams:
         if kernel not in self._KERNEL_FLAGS:
