@@ -377,18 +377,30 @@ GIK_HD void hand_error(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], 
   for (int i = 0; i < 6; ++i) e[i] = F2(el[i], er[i]);
 }
 
-// One hand's share of the damped least-squares step.  Returns u = A^T G^-1 e, w = A^T G^-1 c over the six
-// arm joints (G = A A^T + lambda I, A = arm block, c = chest column) and this hand's c.G^-1 e, c.G^-1 c.
+// One hand's share of the damped least-squares step, in two phases around the only coupling between the hands (the
+// chest joint).  With G = A A^T + lambda I = L L^T (A = 6x6 arm block, c = chest column):
+//   phase 1: yf = L^-1 e, zf = L^-1 c, Sy = zf.yf = c.G^-1 e, Sz = zf.zf = c.G^-1 c
+//   [both hands: kappa = dq_chest = (SyL + SyR) / (1 + SzL + SzR), Sherman-Morrison]
+//   phase 2: dq_arm = A^T L^-T (yf - kappa zf)        (= A^T G^-1 (e - kappa c))
+// so the two right-hand sides share the forward substitution and need ONE backward substitution and ONE A^T product.
+template <typename T>
+struct HandState {
+  T A[6][6];     // arm block of the LOCAL Jacobian (columns of the six arm joints)
+  T L[6][6];     // Cholesky factor, strictly lower part (scaled), inv[j] = 1 / L[j][j]
+  T inv[6];
+  T yf[6], zf[6];
+};
+
 template <typename T, int OFF, uint32_t TZ>
-GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive],
-                      const T (&tgt)[12], T lambda, T (&u)[6], T (&w)[6], T& Sy, T& Sz, T& resid2) {
+GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
+                        T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
   T B[9], b[3], A[6][7], e[6];
   hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
   hand_error(B, b, tgt, e);
   resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
 
-  // Cholesky of G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle, in place; inv[j] = 1 / L[j][j]
-  T L[6][6], inv[6];
+  // Cholesky of G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle, in place
+  T (&L)[6][6] = hs.L;
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -403,41 +415,51 @@ GIK_HD void hand_pass(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&s
     T d = L[j][j];
 #pragma unroll
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    inv[j] = rsqrt_(max_(d, Num<T>::kPivotFloor));
+    hs.inv[j] = rsqrt_(max_(d, Num<T>::kPivotFloor));
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       T v = L[i][j];
 #pragma unroll
       for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-      L[i][j] = v * inv[j];
+      L[i][j] = v * hs.inv[j];
     }
   }
-  // two right-hand sides: y = G^-1 e, z = G^-1 c  (c = A[:,0])
-  T y[6], z[6];
+  // forward substitution of both right-hand sides: e and the chest column c = A[:,0]
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     T a = e[j], cc = A[j][0];
 #pragma unroll
-    for (int k = 0; k < j; ++k) { a -= L[j][k] * y[k]; cc -= L[j][k] * z[k]; }
-    y[j] = a * inv[j]; z[j] = cc * inv[j];
+    for (int k = 0; k < j; ++k) { a -= L[j][k] * hs.yf[k]; cc -= L[j][k] * hs.zf[k]; }
+    hs.yf[j] = a * hs.inv[j]; hs.zf[j] = cc * hs.inv[j];
   }
+  Sy = hs.zf[0] * hs.yf[0]; Sz = hs.zf[0] * hs.zf[0];
 #pragma unroll
-  for (int j = 5; j >= 0; --j) {
-    T a = y[j], cc = z[j];
+  for (int i = 1; i < 6; ++i) { Sy += hs.zf[i] * hs.yf[i]; Sz += hs.zf[i] * hs.zf[i]; }
 #pragma unroll
-    for (int k = j + 1; k < 6; ++k) { a -= L[k][j] * y[k]; cc -= L[k][j] * z[k]; }
-    y[j] = a * inv[j]; z[j] = cc * inv[j];
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hs.A[i][k] = A[i][k + 1];
+}
+
+template <typename T>
+GIK_HD void hand_phase2(const HandState<T>& hs, T kappa, T (&dq)[6]) {
+  T t[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) t[j] = hs.yf[j] - kappa * hs.zf[j];
+#pragma unroll
+  for (int j = 5; j >= 0; --j) {      // backward substitution L^T x = t
+    T a = t[j];
+#pragma unroll
+    for (int k = j + 1; k < 6; ++k) a -= hs.L[k][j] * t[k];
+    t[j] = a * hs.inv[j];
   }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    T a = A[0][k + 1] * y[0], cc = A[0][k + 1] * z[0];
+    T a = hs.A[0][k] * t[0];
 #pragma unroll
-    for (int i = 1; i < 6; ++i) { a += A[i][k + 1] * y[i]; cc += A[i][k + 1] * z[i]; }
-    u[k] = a; w[k] = cc;
+    for (int i = 1; i < 6; ++i) a += hs.A[i][k] * t[i];
+    dq[k] = a;
   }
-  Sy = A[0][0] * y[0]; Sz = A[0][0] * z[0];   // this hand's share of c.G^-1 e and c.G^-1 c
-#pragma unroll
-  for (int i = 1; i < 6; ++i) { Sy += A[i][0] * y[i]; Sz += A[i][0] * z[i]; }
 }
 
 // Sherman-Morrison coupling of the two arm blocks through the shared chest joint: dq_chest = c.D^-1 e / (1 + c.D^-1 c)
@@ -452,16 +474,17 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
   T cs[kActive], sn[kActive];
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
-  T uL[6], wL[6], uR[6], wR[6], SyL, SzL, SyR, SzR;
-  hand_pass<T, 0, TZ>(tab.arm[0], cs, sn, tgt[0], lambda, uL, wL, SyL, SzL, resid2L);
-  hand_pass<T, 6, TZ>(tab.arm[1], cs, sn, tgt[1], lambda, uR, wR, SyR, SzR, resid2R);
+  HandState<T> hL, hR;
+  T SyL, SzL, SyR, SzR;
+  hand_phase1<T, 0, TZ>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
+  hand_phase1<T, 6, TZ>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
   const T kappa = chest_rate(SyL, SzL, SyR, SzR);
   dq[0] = kappa;
+  T dL[6], dR[6];
+  hand_phase2(hL, kappa, dL);
+  hand_phase2(hR, kappa, dR);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    dq[1 + k] = uL[k] - kappa * wL[k];
-    dq[7 + k] = uR[k] - kappa * wR[k];
-  }
+  for (int k = 0; k < 6; ++k) { dq[1 + k] = dL[k]; dq[7 + k] = dR[k]; }
 }
 
 // fp32 lane kernel: the same iteration with (left, right) packed.  State: chest angle q0, arm angles q2[k] =
@@ -489,13 +512,12 @@ GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[
     sincos_<true>(q2[k].y, sr, cr);
     cs[1 + k] = F2(cl, cr); sn[1 + k] = F2(sl, sr);
   }
-  F2 u[6], w[6], Sy, Sz, r2;
-  hand_pass<F2, 0, TZ>(pt.arm, cs, sn, tgt2, F2(lambda), u, w, Sy, Sz, r2);
+  HandState<F2> hs;
+  F2 Sy, Sz, r2;
+  hand_phase1<F2, 0, TZ>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
   const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
   dq0 = kappa;
-  const F2 nk = F2(-kappa);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) dq2[k] = u[k] + nk * w[k];
+  hand_phase2(hs, F2(kappa), dq2);
   resid2L = r2.x; resid2R = r2.y;
 }
 

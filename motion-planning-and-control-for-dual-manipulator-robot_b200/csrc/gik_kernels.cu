@@ -440,13 +440,15 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     if (exhausted && !__any_sync(0xffffffffu, active)) break;
 
     // ---------------- one descent iteration: this lane's hand ----------------
-    T cs[kActive], sn[kActive], u[6], w[6], Sy, Sz, r;
+    T cs[kActive], sn[kActive], Sy, Sz, r, dqa[6];
+    HandState<T> hs;
 #pragma unroll
     for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
-    hand_pass<T, 0, TZ>(ac, cs, sn, tgt, a.lambda, u, w, Sy, Sz, r);
+    hand_phase1<T, 0, TZ>(ac, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
     const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
     const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
     const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
+    hand_phase2(hs, kappa, dqa);
     const T rL = h ? r_o : r, rR = h ? r : r_o;
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
     const bool done = ok || (it >= a.max_iters);
@@ -455,7 +457,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
 #pragma unroll
       for (int k = 0; k < 6; ++k)
-        q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * (u[k] - kappa * w[k])), tab.hi[off + k]);
+        q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * dqa[k]), tab.hi[off + k]);
       ++it;
     } else if (active) {
       const bool batch = (MODE == MODE_BATCH);
