@@ -417,17 +417,12 @@ def run_b200(args):
         n = wl.solves
         q_host = torch.zeros((n, 15), dtype=dtype).pin_memory()
         pose_host = wl.pose_rows.cpu().pin_memory()
-        q_res = torch.empty((n, 15), dtype=dtype).pin_memory()
-        c_res = torch.empty((n,), dtype=torch.bool).pin_memory()
 
         def e2e_step():
-            qd = q_host.to(dev, non_blocking=True)
-            pd = pose_host.to(dev, non_blocking=True)
-            qq, cc = gik_b200.computeqgrasppose_batch(solver, qd, pd, dtype=dtype)
-            q_res.copy_(qq, non_blocking=True)
-            c_res.copy_(cc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return bool(c_res[0])
+            # public API, HOST tensors in and out: H2D of q_init/pose, the solve and D2H of q/converged all happen
+            # inside this call (pipelined over slabs by GraspIK.solve_host); it returns when the results are in host memory
+            qq, cc = gik_b200.computeqgrasppose_batch(solver, q_host, pose_host, dtype=dtype)
+            return bool(cc[0])
 
         for _ in range(2):
             e2e_step()
@@ -445,7 +440,7 @@ def run_b200(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world * args.steps / (te.item() * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(n * (15 + 12) * esz), "d2h_bytes_per_step": int(n * (15 * esz + 1)),
-               "api": "computeqgrasppose_batch (pinned host row-major in/out)"}
+               "api": "computeqgrasppose_batch(host tensors) -> host tensors (pinned row-major in/out, 4 pipelined slabs)"}
 
     extra = wl.extra() if hasattr(wl, "extra") else {}
     if rank != 0:

@@ -370,6 +370,67 @@ class GraspIK:
         return res
 
 
+def _pinned(cache, key, shape, dtype):
+    t = cache.get(key)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        cache[key] = t
+    return t
+
+
+def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
+               chunks=4, return_info=False):
+    """Host-buffer entry: q_init [B,nq] (or [nq]) and pose [B,12|4x4|7|3] are CPU tensors / arrays; returns CPU tensors
+    (q [B,nq], converged bool [B][, SolveInfo]) in pinned memory owned by the solver (valid until the next call).
+    The batch is cut into `chunks` slabs that are pipelined over two CUDA streams: while slab k is being solved, slab
+    k+1 is copied in (H2D) and slab k-1 is copied out (D2H); a persistent solve kernel hands its SMs to the next
+    slab's kernel as its own blocks retire, so the slabs' tails overlap as well."""
+    dev = self.device
+    p12 = as_pose12(pose, dtype=dtype, device="cpu")
+    B = p12.shape[0]
+    qi = torch.as_tensor(q_init).to(dtype)
+    if qi.dim() == 1:
+        qi = qi.unsqueeze(0)
+    if qi.shape[0] == 1 and B != 1:
+        qi = qi.expand(B, self.nq)
+    cache = self.__dict__.setdefault("_host_cache", {})
+    q_in = qi if qi.is_pinned() else _pinned(cache, "q_in", (B, self.nq), dtype).copy_(qi)
+    p_in = p12 if p12.is_pinned() else _pinned(cache, "p_in", (B, 12), dtype).copy_(p12)
+    q_out = _pinned(cache, "q_out", (B, self.nq), dtype)
+    c_out = _pinned(cache, "c_out", (B,), torch.bool)
+    it_out = _pinned(cache, "it_out", (B,), torch.int32) if return_info else None
+    r_out = _pinned(cache, "r_out", (B, 2), dtype) if return_info else None
+    if B == 0:
+        return (q_out, c_out) + ((SolveInfo(it_out, r_out),) if return_info else ())
+    chunks = max(1, min(int(chunks), B))
+    streams = cache.get("streams")
+    if streams is None:
+        streams = cache["streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    cur = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(cur)
+    bounds = [(B * k) // chunks for k in range(chunks + 1)]
+    for k in range(chunks):
+        lo, hi = bounds[k], bounds[k + 1]
+        st = streams[k % 2]
+        st.wait_event(start)
+        with torch.cuda.stream(st):
+            qd = q_in[lo:hi].to(dev, non_blocking=True).t().contiguous()
+            pd = p_in[lo:hi].to(dev, non_blocking=True).t().contiguous()
+            q, conv, iters, resid = self.solve_soa(qd, pd, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
+            q_out[lo:hi].copy_(q.t(), non_blocking=True)
+            c_out[lo:hi].copy_(conv.bool(), non_blocking=True)
+            if return_info:
+                it_out[lo:hi].copy_(iters, non_blocking=True)
+                r_out[lo:hi].copy_(resid.t(), non_blocking=True)
+    for st in streams:
+        cur.wait_stream(st)
+    cur.synchronize()          # results are host memory: the call returns when they are there
+    return (q_out, c_out) + ((SolveInfo(it_out, r_out),) if return_info else ())
+
+
+GraspIK.solve_host = solve_host
+
 _default = {}
 
 

@@ -397,3 +397,23 @@ def test_full_size_properties_fp32(solver, table):
     a, b = n // 8, n // 4
     qs, convs, _, _ = solver.solve_soa(q0[:, a:b].contiguous(), pose[:, a:b].contiguous())
     assert torch.equal(qs, q[:, a:b]) and torch.equal(convs, conv[a:b])
+
+
+def test_host_pipeline_equals_device_path(solver):
+    # CPU tensors in -> CPU tensors out (GraspIK.solve_host: slabs pipelined over two streams) == the device path
+    import gik_b200
+    n = 70001
+    P = torch.from_numpy(make_poses(n, 81)).float()
+    q_h, ok_h, info_h = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), P, dtype=torch.float32, return_info=True)
+    assert not q_h.is_cuda and q_h.is_pinned() and q_h.shape == (n, 15)
+    q_d, ok_d, info_d = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15, device="cuda:0"), P.cuda(),
+                                                         dtype=torch.float32, return_info=True)
+    # the slabs (17.5k problems) run the pair kernel, the whole batch the packed lane kernel: round-off level agreement
+    assert (ok_h == ok_d.cpu()).float().mean() >= 0.999
+    both = ok_h & ok_d.cpu()
+    d = (q_h[both] - q_d.cpu()[both]).abs().max(dim=1).values
+    assert torch.quantile(d, 0.995) < 1e-3
+    # same slab size on the device path -> identical bits
+    q_s, ok_s = solver.solve(torch.zeros(15), P[:17500].cuda(), dtype=torch.float32)
+    assert torch.equal(q_s.cpu(), q_h[:17500]) and torch.equal(ok_s.cpu(), ok_h[:17500])
+    assert (info_h.iters[:17500] == info_d.iters.cpu()[:17500]).float().mean() > 0.99
