@@ -440,7 +440,7 @@ def run_b200(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n * world * args.steps / (te.item() * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(n * (15 + 12) * esz), "d2h_bytes_per_step": int(n * (15 * esz + 1)),
-               "api": "computeqgrasppose_batch(host tensors) -> host tensors (pinned row-major in/out, 4 pipelined slabs)"}
+               "api": "computeqgrasppose_batch(host tensors) -> host tensors (pinned row-major in/out; one launch, inputs streamed by the copy engine, results stored to host memory by the kernel)"}
 
     extra = wl.extra() if hasattr(wl, "extra") else {}
     if rank != 0:

@@ -112,6 +112,19 @@ int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double*
                   const gik_params_t* params, double* q_out, uint8_t* converged, int32_t* iters,
                   double* resid, void* stream);
 
+/* K3 with ROW-MAJOR I/O and streamed input, for host-resident batches (the layout of the Python API: q [n][nq],
+ * pose [n][12]).  q_init / pose are DEVICE staging buffers; `ready` (device, may be NULL = everything resident) counts
+ * the leading problems already copied in -- the caller advances it on its copy stream after each slab, so the copy
+ * engine fills the staging buffers while the kernel is already solving (a lane refill waits only if it runs ahead of
+ * the copies).  q_out [n][nq], converged [n], iters [n] and resid [n][2] (iters / resid may be NULL) may be PINNED
+ * HOST memory (UVA): results are stored straight over PCIe from the kernel, so no device-to-host copy follows it. */
+int gik_solve_rows_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* params,
+                       float* q_out, uint8_t* converged, int32_t* iters, float* resid,
+                       const unsigned long long* ready, void* stream);
+int gik_solve_rows_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* params,
+                       double* q_out, uint8_t* converged, int32_t* iters, double* resid,
+                       const unsigned long long* ready, void* stream);
+
 /* K3 fused with its all-gather (multi-GPU): the same solve, but each rank's kernel stores its
  * results straight into the result arrays of ALL ranks through peer-mapped pointers (NVLink / NVSwitch P2P stores from
  * the kernel's epilogue), so no collective follows the kernel.  q_all[p] / conv_all[p] are HOST arrays of n_peers

@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"gik_fk_{sfx}").argtypes = [_P, _I64, _P, _P, _P]
         getattr(L, f"gik_jac_{sfx}").argtypes = [_P, _I64, _P, _P, _P]
         getattr(L, f"gik_solve_{sfx}").argtypes = [_P, _I64, _P, _P, PP, _P, _P, _P, _P, _P]
+        getattr(L, f"gik_solve_rows_{sfx}").argtypes = [_P, _I64, _P, _P, PP, _P, _P, _P, _P, _P, _P]
         getattr(L, f"gik_solve_scatter_{sfx}").argtypes = [_P, _I64, _P, _P, PP, _I32, ctypes.POINTER(_P),
                                                             ctypes.POINTER(_P), _I64, _I64, _P, _P, _P]
         getattr(L, f"gik_best_of_{sfx}").argtypes = [_P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]
@@ -107,7 +108,7 @@ def lib() -> ctypes.CDLL:
 EXPORTS = [
     "gik_default_params", "gik_create", "gik_destroy",
     "gik_fk_f32", "gik_fk_f64", "gik_jac_f32", "gik_jac_f64", "gik_solve_f32", "gik_solve_f64",
-    "gik_solve_scatter_f32", "gik_solve_scatter_f64", "gik_best_of_f32", "gik_best_of_f64", "gik_project_edges_f32", "gik_project_edges_f64",
+    "gik_solve_rows_f32", "gik_solve_rows_f64", "gik_solve_scatter_f32", "gik_solve_scatter_f64", "gik_best_of_f32", "gik_best_of_f64", "gik_project_edges_f32", "gik_project_edges_f64",
     "gik_scene_attach", "gik_collision_f32", "gik_collision_f64", "gik_clearance_f32", "gik_clearance_f64",
     "gik_cube_collision_f32", "gik_cube_collision_f64",
     "gik_flops_per_iter", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",

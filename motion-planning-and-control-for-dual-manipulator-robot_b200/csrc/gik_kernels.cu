@@ -45,7 +45,11 @@ struct SolveArgs {
   T* q_dst[GIK_MAX_PEERS];
   uint8_t* conv_dst[GIK_MAX_PEERS];
   int32_t n_dst;
-  int64_t out_n, out_off;
+  int64_t out_off;
+  // element (component c, problem i) of an array lives at ptr[c * sc + i * si]: SoA [C][n] = (n, 1), rows [n][C] = (1, C)
+  int64_t q_sc, q_si, pose_sc, pose_si, out_sc, out_si, res_sc, res_si;
+  // streamed input (host-resident batches): problems [0, *ready) are resident; a refill waits for the ones it takes
+  const unsigned long long* ready;
   int32_t* iters;       // [n] or null (edges: iters_total)
   T* resid;             // [2][n] or null
   // edge mode
@@ -62,9 +66,18 @@ struct SolveArgs {
 };
 
 template <typename T>
-__device__ __forceinline__ void load_cube(const T* pose, int64_t n, int64_t idx, T (&cube)[12]) {
+__device__ __forceinline__ void load_cube(const T* pose, int64_t sc, int64_t si, int64_t idx, T (&cube)[12]) {
 #pragma unroll
-  for (int c = 0; c < 12; ++c) cube[c] = __ldg(pose + (int64_t)c * n + idx);
+  for (int c = 0; c < 12; ++c) cube[c] = __ldg(pose + (int64_t)c * sc + idx * si);
+}
+
+// the problems a refill is about to take must be resident (streamed input); no-op for device-resident batches
+template <typename T>
+__device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned long long upto) {
+  if (a.ready) {
+    if (upto > (unsigned long long)a.n) upto = (unsigned long long)a.n;
+    while (*(const volatile unsigned long long*)a.ready < upto) __nanosleep(200);
+  }
 }
 
 template <typename T, int MODE, uint32_t TZ>
@@ -103,6 +116,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
+      wait_resident(a, base + __popc(need));
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
         if (cand < n) {
@@ -110,9 +124,9 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           active = true;
           it = 0;
 #pragma unroll
-          for (int i = 0; i < kActive; ++i) q[i] = __ldg(a.q_init + (int64_t)tab.act_q[i] * n + idx);
+          for (int i = 0; i < kActive; ++i) q[i] = __ldg(a.q_init + (int64_t)tab.act_q[i] * a.q_sc + idx * a.q_si);
           T cube[12];
-          load_cube(a.pose, n, idx, cube);
+          load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
             nsteps = __ldg(a.num_steps + idx);
             step = 1;
@@ -120,7 +134,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
             T cb[12], xi[6], ca[12];
 #pragma unroll
             for (int c = 0; c < 12; ++c) ca[c] = cube[c];
-            load_cube(a.pose_b, n, idx, cb);
+            load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
             se3_delta(ca, cb, xi);
             se3_advance(ca, xi, T(1) / T(nsteps), cube);
             if (nsteps < 1) {  // nothing to march: reference loop body never runs (path.py:137)
@@ -152,17 +166,17 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
           T* qo = a.q_dst[d];
 #pragma unroll
-          for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_n + col] = q[i];
+          for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_sc + col * a.out_si] = q[i];
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
-            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
-            qo[(int64_t)j * a.out_n + col] = v;
+            qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
           a.conv_dst[d][col] = ok ? 1 : 0;
         }
         if (a.iters) a.iters[idx] = it;
-        if (a.resid) { a.resid[idx] = sqrt_(rL); a.resid[n + idx] = sqrt_(rR); }
+        if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
       } else {
         it_total += it;
@@ -173,7 +187,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
-            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
             dst[(int64_t)j * n + idx] = v;
           }
@@ -182,8 +196,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           ++step;
           it = 0;
           T ca[12], cb[12], xi[6], cube[12];
-          load_cube(a.pose, n, idx, ca);
-          load_cube(a.pose_b, n, idx, cb);
+          load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
+          load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
           se3_delta(ca, cb, xi);
           se3_advance(ca, xi, T(step) / T(nsteps), cube);
           hook_target(tab.arm[0], cube, tgt[0]);
@@ -231,12 +245,12 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 #pragma unroll
     for (int c = 0; c < 12; ++c) tgt2[c] = F2(tl[c], tr[c]);
   };
-  auto store_q = [&](T* dst, int64_t ld, int64_t col) {
-    dst[(int64_t)tab.act_q[0] * ld + col] = q0;
+  auto store_q = [&](T* dst, int64_t sc, int64_t si, int64_t col) {
+    dst[(int64_t)tab.act_q[0] * sc + col * si] = q0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      dst[(int64_t)tab.act_q[1 + k] * ld + col] = q2[k].x;
-      dst[(int64_t)tab.act_q[7 + k] * ld + col] = q2[k].y;
+      dst[(int64_t)tab.act_q[1 + k] * sc + col * si] = q2[k].x;
+      dst[(int64_t)tab.act_q[7 + k] * sc + col * si] = q2[k].y;
     }
   };
 
@@ -260,18 +274,19 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
+      wait_resident(a, base + __popc(need));
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
         if (cand < n) {
           idx = cand;
           active = true;
           it = 0;
-          q0 = __ldg(a.q_init + (int64_t)tab.act_q[0] * n + idx);
+          q0 = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
           for (int k = 0; k < 6; ++k)
-            q2[k] = F2(__ldg(a.q_init + (int64_t)tab.act_q[1 + k] * n + idx), __ldg(a.q_init + (int64_t)tab.act_q[7 + k] * n + idx));
+            q2[k] = F2(__ldg(a.q_init + (int64_t)tab.act_q[1 + k] * a.q_sc + idx * a.q_si), __ldg(a.q_init + (int64_t)tab.act_q[7 + k] * a.q_sc + idx * a.q_si));
           T cube[12];
-          load_cube(a.pose, n, idx, cube);
+          load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
             nsteps = __ldg(a.num_steps + idx);
             step = 1;
@@ -279,7 +294,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
             T cb[12], xi[6], ca[12];
 #pragma unroll
             for (int c = 0; c < 12; ++c) ca[c] = cube[c];
-            load_cube(a.pose_b, n, idx, cb);
+            load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
             se3_delta(ca, cb, xi);
             se3_advance(ca, xi, T(1) / T(nsteps), cube);
             if (nsteps < 1) {  // nothing to march: reference loop body never runs (path.py:137)
@@ -313,27 +328,27 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         const int64_t col = a.out_off + idx;
         for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
           T* qo = a.q_dst[d];
-          store_q(qo, a.out_n, col);
+          store_q(qo, a.out_sc, a.out_si, col);
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
-            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
-            qo[(int64_t)j * a.out_n + col] = v;
+            qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
           a.conv_dst[d][col] = ok ? 1 : 0;
         }
         if (a.iters) a.iters[idx] = it;
-        if (a.resid) { a.resid[idx] = sqrt_(rL); a.resid[n + idx] = sqrt_(rR); }
+        if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
       } else {
         it_total += it;
         if (ok) {
           T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n;
-          store_q(dst, n, idx);
+          store_q(dst, n, 1, idx);
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
-            T v = __ldg(a.q_init + (int64_t)j * n + idx);
+            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
             dst[(int64_t)j * n + idx] = v;
           }
@@ -342,8 +357,8 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
           ++step;
           it = 0;
           T ca[12], cb[12], xi[6], cube[12];
-          load_cube(a.pose, n, idx, ca);
-          load_cube(a.pose_b, n, idx, cb);
+          load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
+          load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
           se3_delta(ca, cb, xi);
           se3_advance(ca, xi, T(step) / T(nsteps), cube);
           set_targets(cube);
@@ -407,17 +422,18 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
+      wait_resident(a, base + __popc(need));
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & lower_pairs);
         if (cand < n) {
           idx = cand;
           active = true;
           it = 0;
-          q[0] = __ldg(a.q_init + (int64_t)tab.act_q[0] * n + idx);
+          q[0] = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) q[1 + k] = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * n + idx);
+          for (int k = 0; k < 6; ++k) q[1 + k] = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * a.q_sc + idx * a.q_si);
           T cube[12];
-          load_cube(a.pose, n, idx, cube);
+          load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
             nsteps = __ldg(a.num_steps + idx);
             step = 1;
@@ -425,7 +441,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
             T cb[12], xi[6], ca[12];
 #pragma unroll
             for (int c = 0; c < 12; ++c) ca[c] = cube[c];
-            load_cube(a.pose_b, n, idx, cb);
+            load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
             se3_delta(ca, cb, xi);
             se3_advance(ca, xi, T(1) / T(nsteps), cube);
             if (nsteps < 1) {
@@ -465,18 +481,18 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
         const bool moved = batch ? (it > 0) : (it_total > 0);
         const int n_dst = batch ? a.n_dst : 1;
-        const int64_t ld = batch ? a.out_n : n, col = batch ? a.out_off + idx : idx;
+        const int64_t ld = batch ? a.out_sc : n, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + idx : idx;
         for (int d = 0; d < n_dst; ++d) {       // batch: 1 destination, or every rank's result array (fused all-gather)
           T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n;
 #pragma unroll
-          for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col] = q[1 + k];
+          for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col * cs_] = q[1 + k];
           if (h == 0) {
-            dst[(int64_t)tab.act_q[0] * ld + col] = q[0];
+            dst[(int64_t)tab.act_q[0] * ld + col * cs_] = q[0];
             for (int p = 0; p < tab.n_passive; ++p) {
               const int j = tab.passive_q[p];
-              T v = __ldg(a.q_init + (int64_t)j * n + idx);
+              T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
               if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
-              dst[(int64_t)j * ld + col] = v;
+              dst[(int64_t)j * ld + col * cs_] = v;
             }
             if (batch) a.conv_dst[d][col] = ok ? 1 : 0;
           }
@@ -484,14 +500,14 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       }
       if (batch) {
         if (h == 0 && a.iters) a.iters[idx] = it;
-        if (a.resid) a.resid[(int64_t)h * n + idx] = sqrt_(r);
+        if (a.resid) a.resid[(int64_t)h * a.res_sc + idx * a.res_si] = sqrt_(r);
         active = false;
       } else if (ok && step < nsteps) {
         ++step;
         it = 0;
         T ca[12], cb[12], xi[6], cube[12];
-        load_cube(a.pose, n, idx, ca);
-        load_cube(a.pose_b, n, idx, cb);
+        load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
+        load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
         se3_delta(ca, cb, xi);
         se3_advance(ca, xi, T(step) / T(nsteps), cube);
         hook_target(ac, cube, tgt);
@@ -736,6 +752,37 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
 }
 
 template <typename T>
+void set_soa(SolveArgs<T>& a, int64_t n_in, int64_t n_out) {
+  a.q_sc = n_in; a.q_si = 1; a.pose_sc = n_in; a.pose_si = 1;
+  a.out_sc = n_out; a.out_si = 1; a.res_sc = n_in; a.res_si = 1;
+  a.ready = nullptr;
+}
+
+// Row-major I/O with streamed input: q_init [n][nq] and pose [n][12] are DEVICE staging buffers being filled slab by
+// slab by the copy engine while the kernel runs (`ready` = device counter of resident leading problems, advanced on
+// the copy stream after each slab); q_out [n][nq], converged [n], iters [n], resid [n][2] may be PINNED HOST memory
+// (UVA): the kernel's stores go straight over PCIe, so no D2H copy follows the kernel.
+template <typename T>
+int rows_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, T* q_out, uint8_t* conv,
+             int32_t* iters, T* resid, const unsigned long long* ready, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0) return GIK_E_SIZE;
+  int rc = check_params(prm);
+  if (rc) return rc;
+  if (n == 0) return GIK_OK;
+  if (!q_init || !pose || !q_out || !conv) return GIK_E_NULL;
+  SolveArgs<T> a{};
+  a.q_init = q_init; a.pose = pose; a.iters = iters; a.resid = resid;
+  a.q_dst[0] = q_out; a.conv_dst[0] = conv; a.n_dst = 1; a.out_off = 0;
+  a.n = n;
+  const int nq = h->host.nq;
+  a.q_sc = 1; a.q_si = nq; a.pose_sc = 1; a.pose_si = 12;
+  a.out_sc = 1; a.out_si = nq; a.res_sc = 1; a.res_si = 2;
+  a.ready = ready;
+  return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+}
+
+template <typename T>
 int solve_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, T* q_out,
               uint8_t* conv, int32_t* iters, T* resid, void* stream) {
   if (bad_handle(h)) return GIK_E_HANDLE;
@@ -746,8 +793,9 @@ int solve_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const g
   if (!q_init || !pose || !q_out || !conv) return GIK_E_NULL;
   SolveArgs<T> a{};
   a.q_init = q_init; a.pose = pose; a.iters = iters; a.resid = resid;
-  a.q_dst[0] = q_out; a.conv_dst[0] = conv; a.n_dst = 1; a.out_n = n; a.out_off = 0;
+  a.q_dst[0] = q_out; a.conv_dst[0] = conv; a.n_dst = 1; a.out_off = 0;
   a.n = n;
+  set_soa(a, n, n);
   return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
 }
 
@@ -767,8 +815,9 @@ int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const
     if (!q_all[p] || !conv_all[p]) return GIK_E_NULL;
     a.q_dst[p] = q_all[p]; a.conv_dst[p] = conv_all[p];
   }
-  a.n_dst = n_peers; a.out_n = n_total; a.out_off = offset;
+  a.n_dst = n_peers; a.out_off = offset;
   a.n = n;
+  set_soa(a, n, n_total);
   return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
 }
 
@@ -785,6 +834,7 @@ int edges_api(gik_handle_t h, int64_t n, int32_t max_steps, const T* q_start, co
   SolveArgs<T> a{};
   a.q_init = q_start; a.pose = pose_a; a.pose_b = pose_b; a.num_steps = num_steps; a.q_out = q_path;
   a.n_valid = n_valid; a.iters = iters_total; a.max_steps = max_steps; a.n = n;
+  set_soa(a, n, n);
   return launch_solve<T, MODE_EDGES>(h, a, prm, stream);
 }
 
@@ -911,6 +961,15 @@ int gik_solve_f32(gik_handle_t h, int64_t n, const float* q_init, const float* p
 int gik_solve_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p,
                   double* q_out, uint8_t* conv, int32_t* iters, double* resid, void* s) {
   return solve_api<double>(h, n, q_init, pose, p, q_out, conv, iters, resid, s);
+}
+
+int gik_solve_rows_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p, float* q_out,
+                       uint8_t* conv, int32_t* iters, float* resid, const unsigned long long* ready, void* s) {
+  return rows_api<float>(h, n, q_init, pose, p, q_out, conv, iters, resid, ready, s);
+}
+int gik_solve_rows_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p, double* q_out,
+                       uint8_t* conv, int32_t* iters, double* resid, const unsigned long long* ready, void* s) {
+  return rows_api<double>(h, n, q_init, pose, p, q_out, conv, iters, resid, ready, s);
 }
 
 int gik_solve_scatter_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p,

@@ -379,12 +379,17 @@ def _pinned(cache, key, shape, dtype):
 
 
 def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
-               chunks=4, return_info=False):
+               slabs=4, return_info=False, kernel=None):
     """Host-buffer entry: q_init [B,nq] (or [nq]) and pose [B,12|4x4|7|3] are CPU tensors / arrays; returns CPU tensors
     (q [B,nq], converged bool [B][, SolveInfo]) in pinned memory owned by the solver (valid until the next call).
-    The batch is cut into `chunks` slabs that are pipelined over two CUDA streams: while slab k is being solved, slab
-    k+1 is copied in (H2D) and slab k-1 is copied out (D2H); a persistent solve kernel hands its SMs to the next
-    slab's kernel as its own blocks retire, so the slabs' tails overlap as well."""
+
+    ONE solve launch (gik_solve_rows_*), overlapped with its own transfers:
+      * inputs: the copy engine streams the row-major host arrays into device staging buffers slab by slab on a copy
+        stream and advances a device counter after each slab; the kernel is launched as soon as the first (small) slab
+        is in, and a lane refill only waits if it runs ahead of the copies (copies deliver ~20x faster than the solver
+        consumes, so in practice never);
+      * outputs: the kernel stores q / converged (/ iters / resid) of each finished problem straight into the pinned
+        host arrays (UVA stores over PCIe), so no device-to-host copy follows the kernel."""
     dev = self.device
     p12 = as_pose12(pose, dtype=dtype, device="cpu")
     B = p12.shape[0]
@@ -394,39 +399,51 @@ def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, m
     if qi.shape[0] == 1 and B != 1:
         qi = qi.expand(B, self.nq)
     cache = self.__dict__.setdefault("_host_cache", {})
-    q_in = qi if qi.is_pinned() else _pinned(cache, "q_in", (B, self.nq), dtype).copy_(qi)
-    p_in = p12 if p12.is_pinned() else _pinned(cache, "p_in", (B, 12), dtype).copy_(p12)
+    q_in = qi if (qi.is_pinned() and qi.is_contiguous()) else _pinned(cache, "q_in", (B, self.nq), dtype).copy_(qi)
+    p_in = p12 if (p12.is_pinned() and p12.is_contiguous()) else _pinned(cache, "p_in", (B, 12), dtype).copy_(p12)
     q_out = _pinned(cache, "q_out", (B, self.nq), dtype)
-    c_out = _pinned(cache, "c_out", (B,), torch.bool)
+    c_out = _pinned(cache, "c_out", (B,), torch.uint8)
     it_out = _pinned(cache, "it_out", (B,), torch.int32) if return_info else None
     r_out = _pinned(cache, "r_out", (B, 2), dtype) if return_info else None
     if B == 0:
-        return (q_out, c_out) + ((SolveInfo(it_out, r_out),) if return_info else ())
-    chunks = max(1, min(int(chunks), B))
-    streams = cache.get("streams")
-    if streams is None:
-        streams = cache["streams"] = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        return (q_out, c_out.view(torch.bool)) + ((SolveInfo(it_out, r_out),) if return_info else ())
+    key = (B, dtype)
+    if cache.get("stage_key") != key:
+        cache["stage_key"] = key
+        cache["dq"] = torch.empty((B, self.nq), dtype=dtype, device=dev)
+        cache["dp"] = torch.empty((B, 12), dtype=dtype, device=dev)
+        cache["ready"] = torch.zeros((1,), dtype=torch.int64, device=dev)
+    dq, dp, ready = cache["dq"], cache["dp"], cache["ready"]
+    copy_stream = cache.get("copy_stream")
+    if copy_stream is None:
+        copy_stream = cache["copy_stream"] = torch.cuda.Stream(device=dev)
+    # slab boundaries: a small first slab so the kernel starts early, the rest in equal parts
+    slabs = max(1, int(slabs))
+    first = min(B, max(1 << 16, B // 16)) if slabs > 1 else B
+    bounds = [0, first] + [first + ((B - first) * k) // (slabs - 1) for k in range(1, slabs)] if slabs > 1 and first < B else [0, B]
+    marks = _pinned(cache, "marks", (len(bounds) - 1,), torch.int64)
+    marks.copy_(torch.tensor(bounds[1:], dtype=torch.int64))
     cur = torch.cuda.current_stream(dev)
-    start = torch.cuda.Event()
-    start.record(cur)
-    bounds = [(B * k) // chunks for k in range(chunks + 1)]
-    for k in range(chunks):
-        lo, hi = bounds[k], bounds[k + 1]
-        st = streams[k % 2]
-        st.wait_event(start)
-        with torch.cuda.stream(st):
-            qd = q_in[lo:hi].to(dev, non_blocking=True).t().contiguous()
-            pd = p_in[lo:hi].to(dev, non_blocking=True).t().contiguous()
-            q, conv, iters, resid = self.solve_soa(qd, pd, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
-            q_out[lo:hi].copy_(q.t(), non_blocking=True)
-            c_out[lo:hi].copy_(conv.bool(), non_blocking=True)
-            if return_info:
-                it_out[lo:hi].copy_(iters, non_blocking=True)
-                r_out[lo:hi].copy_(resid.t(), non_blocking=True)
-    for st in streams:
-        cur.wait_stream(st)
-    cur.synchronize()          # results are host memory: the call returns when they are there
-    return (q_out, c_out) + ((SolveInfo(it_out, r_out),) if return_info else ())
+    copy_stream.wait_stream(cur)                      # staging buffers may still be read by a previous launch
+    first_in = torch.cuda.Event()
+    with torch.cuda.stream(copy_stream):
+        ready.zero_()
+        for k in range(len(bounds) - 1):
+            lo, hi = bounds[k], bounds[k + 1]
+            dq[lo:hi].copy_(q_in[lo:hi], non_blocking=True)
+            dp[lo:hi].copy_(p_in[lo:hi], non_blocking=True)
+            ready.copy_(marks[k:k + 1], non_blocking=True)
+            if k == 0:
+                first_in.record(copy_stream)
+    cur.wait_event(first_in)
+    prm = self._params(eps, dt, max_iters, damping, kernel)
+    f = getattr(self._lib, f"gik_solve_rows_{_sfx(dtype)}")
+    _cabi.check(f(self._h, B, self._ptr(dq), self._ptr(dp), ctypes.byref(prm), self._ptr(q_out), self._ptr(c_out),
+                  self._ptr(it_out), self._ptr(r_out), self._ptr(ready), self._stream()), "gik_solve_rows")
+    self.launches += 1
+    cur.synchronize()          # results are host memory: the call returns when the kernel has stored them
+    copy_stream.synchronize()
+    return (q_out, c_out.view(torch.bool)) + ((SolveInfo(it_out, r_out),) if return_info else ())
 
 
 GraspIK.solve_host = solve_host
