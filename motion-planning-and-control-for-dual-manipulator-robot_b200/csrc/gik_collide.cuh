@@ -140,7 +140,9 @@ GIK_HD bool gjk_intersect(const Shape<T>& A, const Shape<T>& B, T margin) {
 template <typename T>
 struct TreeConst {
   int32_t nq;
+  int32_t max_depth;               // depth of the deepest joint (root joints have depth 0)
   int32_t parent[GIK_MAX_NQ];
+  int32_t depth[GIK_MAX_NQ];
   int32_t axis[GIK_MAX_NQ];
   T jR[GIK_MAX_NQ][9];
   T jp[GIK_MAX_NQ][3];

@@ -1,5 +1,5 @@
 // gik_collide_impl.cuh -- collision kernels + their C ABI (included at the end of gik_kernels.cu: one translation
-// unit, one library).  Mapping: ONE CONFIGURATION PER WARP.  Lane 0 walks the kinematic tree into shared memory,
+// unit, one library).  Mapping: ONE CONFIGURATION PER WARP.  The kinematic tree is walked level by level (one joint per lane),
 // the lanes place the geometries (oMg = oMi[parent] * placement, pin.updateGeometryPlacements), then the collision
 // pairs are dealt round-robin to the 32 lanes: bounding-sphere rejection first, boolean GJK on the survivors, one
 // __any_sync per round for the early exit.  The scene (geometries, pair lists) lives in global memory and is read
@@ -22,14 +22,27 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
   const int nq = sc->tree.nq, ng = sc->n_geoms;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
-    if (q && lane == 0) {
-      for (int j = 0; j < nq; ++j) {
-        const int par = sc->tree.parent[j];
-        joint_placement(sc->tree, j, par < 0 ? (const T*)nullptr : &s_oMi[w][par][0], __ldg(q + (int64_t)j * n + i),
-                        &s_oMi[w][j][0]);
+    if (q) {
+      // tree FK, level by level: lane j first builds its joint's local transform jointPlacement * Rot(axis, q_j), then
+      // the joints of depth d (all independent) are composed with their parents' world placements of depth d - 1
+      T L[12];
+      int par = -1, dep = -1;
+      if (lane < nq) {
+        joint_placement(sc->tree, lane, (const T*)nullptr, __ldg(q + (int64_t)lane * n + i), L);
+        par = sc->tree.parent[lane]; dep = sc->tree.depth[lane];
+      }
+      for (int d = 0; d <= sc->tree.max_depth; ++d) {
+        if (dep == d) {
+          if (par < 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_oMi[w][lane][k] = L[k];
+          } else {
+            se3_mul12(&s_oMi[w][par][0], L, &s_oMi[w][lane][0]);
+          }
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
     for (int g = lane; g < ng; g += 32) {
       const DevGeom<T>& G = sc->g[g];
       T P[12];

@@ -153,6 +153,8 @@ inline void fill_dev_scene(const gik_table_t& t, const gik_scene_t& s, DevScene<
   d.tree.nq = t.nq;
   for (int i = 0; i < t.nq; ++i) {
     d.tree.parent[i] = t.parent[i];
+    d.tree.depth[i] = t.parent[i] < 0 ? 0 : d.tree.depth[t.parent[i]] + 1;     // parents are listed first
+    if (d.tree.depth[i] > d.tree.max_depth) d.tree.max_depth = d.tree.depth[i];
     d.tree.axis[i] = t.axis[i];
     for (int k = 0; k < 9; ++k) d.tree.jR[i][k] = (T)t.joint_R[i][k];
     for (int k = 0; k < 3; ++k) d.tree.jp[i][k] = (T)t.joint_p[i][k];

@@ -418,3 +418,41 @@ def test_host_pipeline_equals_device_path(solver):
     q_h, ok_h = gik_b200.computeqgrasppose_batch(solver, Q0, P, dtype=torch.float64)
     q_d, ok_d = gik_b200.computeqgrasppose_batch(solver, Q0.cuda(), P.cuda(), dtype=torch.float64)
     assert torch.equal(q_h, q_d.cpu()) and torch.equal(ok_h, ok_d.cpu())
+
+
+def test_other_robot_tables_generic_instantiation(table, c_oracle):
+    # a table of the same topology but other dimensions (no zero translation components, other hand / hook frames,
+    # narrower limits) runs the GENERIC kernel instantiations (TZ = 0), not the Nextage-specialised ones
+    import copy
+    import gik_b200
+    rng = np.random.default_rng(17)
+    t = copy.deepcopy(table)
+    t.joint_p = t.joint_p + rng.uniform(0.004, 0.02, size=t.joint_p.shape) * np.sign(rng.normal(size=t.joint_p.shape))
+    t.hand_R = np.array([rot_rpy(0.1, -0.05, 1.2), rot_rpy(-0.08, 0.03, 1.9)])
+    t.hand_p = t.hand_p + rng.normal(scale=0.01, size=(2, 3))
+    t.hook_R = np.array([rot_rpy(0.02, 0.0, 0.1), rot_rpy(0.0, 0.03, -3.0)])
+    t.lower = t.lower * 0.9; t.upper = t.upper * 0.9
+    t.meta = {"source": "test"}
+    s = gik_b200.GraspIK(t, "cuda:0")
+    tc = t.to_c()
+    n = 700
+    P = make_poses(n, 91)
+    qo, oko, ito, _ = c_oracle.solve(tc, np.zeros((n, 15)), P)
+    for kern in ("lane", "pair"):
+        q, ok, info = s.solve(torch.zeros(15), _t(P), dtype=torch.float64, return_info=True, kernel=kern)
+        ok = ok.cpu().numpy(); q = q.cpu().numpy()
+        assert (ok == oko).mean() >= 0.995 and 0.2 < oko.mean() < 0.95
+        both = ok & oko
+        _assert_q_close(q[both], qo[both], 1e-9, frac=0.99, tol_outlier=5e-2)
+        assert (info.iters.cpu().numpy()[both] == ito[both]).mean() >= 0.99
+    q32, ok32 = s.solve(torch.zeros(15), _t(P), dtype=torch.float32, kernel="lane")     # packed kernel, TZ = 0
+    assert (ok32.cpu().numpy() == oko).mean() >= 0.99
+    R, p = c_oracle.fk(tc, qo)
+    Rg, pg = s.fk(_t(qo))
+    assert np.abs(pg.cpu().numpy() - p).max() < 1e-9 and np.abs(Rg.cpu().numpy() - R).max() < 1e-9
+    s.close()
+    # a different topology is rejected, not solved slowly
+    bad = copy.deepcopy(table); bad.axis = bad.axis.copy(); bad.axis[5] = 0
+    from gik_b200 import _cabi
+    with pytest.raises(_cabi.GikError, match="topology|fast path"):
+        gik_b200.GraspIK(bad, "cuda:0")
