@@ -163,3 +163,22 @@ def test_rrt_connect_driver_end_to_end(solver, table, table_c, scene_c, c_oracle
     mid = 0.5 * (p[:, 0] + p[:, 1])
     jumps = np.linalg.norm(np.diff(mid, axis=0), axis=1)
     assert np.quantile(jumps, 0.9) < 0.03
+
+
+def test_success_rate_experiment_matches_oracle(solver, table_c, scene_c, c_oracle):
+    # inverse_geometry_TESTS.py:474-561 in batch form: the same placements through the oracle give the same tally
+    from gik_b200 import experiments
+    a = (np.eye(3), np.array([0.33, -0.3, 0.93])); b = (np.eye(3), np.array([0.4, 0.11, 0.93]))
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    res = experiments.grasp_success_rate(solver, a, b, std_devs=[(0.1, 0.1, 0.1), (0.4, 0.4, 0.4)], trials=48, generator=g)
+    assert [r[2] for r in res] == [48, 48] and all(0.0 <= r[1] <= 100.0 for r in res)
+    # replay the first spread's placements through the CPU oracle
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    pl = experiments.sample_gaussian_placements(48 * 4, a, b, (0.1, 0.1, 0.1), device="cuda:0", generator=g).cpu().numpy()
+    lo = np.minimum(a[1], b[1]) - 0.14; hi = np.maximum(a[1], b[1]) + 0.14
+    assert (pl >= lo - 1e-12).all() and (pl <= hi + 1e-12).all()
+    P = np.zeros((len(pl), 12)); P[:, [0, 4, 8]] = 1; P[:, 9:] = pl
+    free = c_oracle.scene_distance(table_c, scene_c, None, P, mode=2) > 0
+    P = P[free][:48]
+    _, ok, _ = c_oracle.solve_success(table_c, scene_c, np.zeros((len(P), 15)), P)
+    assert abs(100.0 * ok.mean() - res[0][1]) < 1e-9
