@@ -49,5 +49,5 @@ def grasp_success_rate(robot, cubeplacementq0, cubeplacementqgoal, std_devs=STD_
         P = torch.cat(kept, 0)
         q0 = torch.zeros((solver.nq, P.shape[0]), dtype=dtype, device=solver.device)
         _, succ, _, _, _ = solver.solve_success_soa(q0, P.t().contiguous(), descend_while_colliding=descend_while_colliding)
-        out.append((tuple(sd), 100.0 * float(succ.float().mean().item()), int(P.shape[0])))
+        out.append((tuple(sd), 100.0 * float(succ.double().mean().item()), int(P.shape[0])))
     return out
