@@ -27,6 +27,7 @@ from .model import KinematicTable, from_pinocchio, nextage_table
 from .ops import DT, EPSILON, MAX_ITERS, GraspIK, as_pose12, default_solver
 
 _solvers = weakref.WeakKeyDictionary()
+_solvers_by_id = {}          # objects that cannot be weakly referenced: id -> (object kept alive, solver)
 
 
 def _is_pinocchio_wrapper(robot) -> bool:
@@ -50,12 +51,18 @@ def solver_for(robot, cube=None, device=None) -> GraspIK:
         return _solvers[key]
     except (KeyError, TypeError):
         pass
+    hit = _solvers_by_id.get(id(key))
+    if hit is not None and hit[0] is key:
+        return hit[1]
+    if not isinstance(robot, KinematicTable) and cube is None:
+        raise ValueError("the first call for a pinocchio robot needs `cube` (its LARM_HOOK / RARM_HOOK frames are part of "
+                         "the flattened table)")
     table = robot if isinstance(robot, KinematicTable) else from_pinocchio(robot, cube)
     s = GraspIK(table, device)
     try:
         _solvers[key] = s
     except TypeError:
-        pass
+        _solvers_by_id[id(key)] = (key, s)
     return s
 
 
@@ -157,7 +164,7 @@ def computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None, *, collision=
 
 def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, eps=EPSILON, dt=DT,
                             max_iters=MAX_ITERS, damping=0.0, restarts=1, generator=None, return_info=False,
-                            collision=False):
+                            collision=False, cube=None):
     """Batched entry point (new).  `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (Nextage).
     q_init [B,nq] or [nq]; cube_pose [B,12|4x4|7|3].  CUDA tensors in -> CUDA tensors out (q [B,nq], converged bool
     [B][, SolveInfo]) with no host synchronisation; CPU tensors in -> CPU tensors out through the pipelined host path
@@ -167,7 +174,7 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
     the reference's full `success` (converged and collision-free on the attached scene, with the reference's
     keep-descending-while-colliding behaviour: GraspIK.solve_success_soa); the default returns `converged` only (the
     north_star's kernel contract; `apply_collision` applies a host-side test afterwards)."""
-    solver = solver_for(robot)
+    solver = solver_for(robot, cube)
     host_in = (not torch.is_tensor(cube_pose) or not cube_pose.is_cuda) and (not torch.is_tensor(q_init) or not q_init.is_cuda)
     if host_in and not collision and restarts <= 1 and torch.is_tensor(cube_pose):
         # CPU tensors in -> CPU (pinned) tensors out, copies pipelined with the solve (GraspIK.solve_host)

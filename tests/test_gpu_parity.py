@@ -456,3 +456,23 @@ def test_other_robot_tables_generic_instantiation(table, c_oracle):
     from gik_b200 import _cabi
     with pytest.raises(_cabi.GikError, match="topology|fast path"):
         gik_b200.GraspIK(bad, "cuda:0")
+
+
+def test_dropin_with_pinocchio_like_objects(table, golden):
+    # the reference's call, duck-typed: RobotWrapper-like `robot` / `cube` (model flattened once with from_pinocchio and
+    # cached per object) and an SE3-like `cubetarget` with .rotation / .translation (inverse_geometry.py:105-113)
+    import types
+    import gik_b200
+    from test_model import _fake_pinocchio
+    robot, cube = _fake_pinocchio(table)
+    robot.q0 = np.zeros(15)
+    for c in golden["cases"]:
+        target = types.SimpleNamespace(rotation=np.array(c["cube_R"], float).reshape(3, 3), translation=np.array(c["cube_p"], float))
+        q, success = gik_b200.computeqgrasppose(robot, robot.q0.copy(), cube, target, None)
+        assert success is True and np.abs(q - np.array(c["q"])).max() < 1e-9
+    s1 = gik_b200.solver_for(robot, cube)
+    assert s1 is gik_b200.solver_for(robot, cube) and s1.table.meta["source"] == "pinocchio"     # flattened once
+    # batched entry on the same objects, host arrays in -> host tensors out
+    P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
+    qb, ok = gik_b200.computeqgrasppose_batch(robot, np.zeros(15), torch.from_numpy(P), dtype=torch.float64)
+    assert ok.all() and np.abs(qb.numpy() - np.array([c["q"] for c in golden["cases"]])).max() < 1e-9
