@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 N_PER_GPU = 1 << 20
 WORKSPACE_LO = (0.20, -0.40, 0.93)
 WORKSPACE_HI = (0.60, 0.40, 1.40)
+SAMPLER_LO = (0.33, -0.30, 1.05)        # the reference sampler's box, path.py:35-37 with config.py:36-37
+SAMPLER_HI = (0.40, 0.11, 1.40)
 METRIC = "dual-arm grasp IK solves/sec"
 _STDOUT = sys.stdout
 
@@ -48,6 +50,8 @@ def parse():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: 'fused' = the solve kernel stores results into every rank's symmetric-memory arrays over "
                          "NVLink (falls back to nccl if symmetric memory is unavailable); 'nccl' = all_gather_into_tensor")
+    ap.add_argument("--box", default="workspace", choices=["workspace", "sampler"],
+                    help="config 2 placement box: the table workspace (default) or the reference sampler's box (path.py:35-37)")
     ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
@@ -87,6 +91,18 @@ def cpu_solve_rate(n_sample, seed=1234):
     c_oracle.solve(tc, np.zeros((n_sample, 15)), P, threads=threads)
     dt = time.perf_counter() - t0
     return n_sample / dt, threads, dt
+
+
+def numpy_solve_rate(n_sample, seed=99):
+    """The numpy restatement (oracle/grasp_ik_np.py: one Python-level call per pinocchio/numpy primitive, like the
+    reference's own loop) on one core -- the closest thing to the reference's Python speed this image can run."""
+    import numpy as np
+    from oracle import grasp_ik_np as o
+    P = host_poses(n_sample, seed)
+    t0 = time.perf_counter()
+    for i in range(n_sample):
+        o.computeqgrasppose(np.zeros(15), np.eye(3), P[i, 9:])
+    return n_sample / (time.perf_counter() - t0)
 
 
 def run_reference(args):
@@ -176,10 +192,10 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
-def workspace_positions(torch, n, dev, dtype, seed):
+def workspace_positions(torch, n, dev, dtype, seed, box="workspace"):
     g = torch.Generator(device=dev).manual_seed(seed)
-    lo = torch.tensor(WORKSPACE_LO, device=dev, dtype=dtype)
-    hi = torch.tensor(WORKSPACE_HI, device=dev, dtype=dtype)
+    lo = torch.tensor(WORKSPACE_LO if box == "workspace" else SAMPLER_LO, device=dev, dtype=dtype)
+    hi = torch.tensor(WORKSPACE_HI if box == "workspace" else SAMPLER_HI, device=dev, dtype=dtype)
     return lo + torch.rand((n, 3), device=dev, dtype=dtype, generator=g) * (hi - lo)
 
 
@@ -198,15 +214,18 @@ class Workload:
 
 
 class Config2(Workload):
-    def __init__(self, torch, solver, n, rank, dtype, seed_base=1000):
+    def __init__(self, torch, solver, n, rank, dtype, seed_base=1000, box="workspace"):
         dev = solver.device
         self.torch, self.solver, self.solves = torch, solver, n
-        self.pose_rows = pose_rows_from(torch, workspace_positions(torch, n, dev, dtype, seed_base + rank))
+        self.pose_rows = pose_rows_from(torch, workspace_positions(torch, n, dev, dtype, seed_base + rank, box))
         self.pose = self.pose_rows.t().contiguous()                 # SoA [12][n]
         self.q0 = torch.zeros((15, n), device=dev, dtype=dtype)     # SoA [15][n]
         self.out = (torch.empty_like(self.q0), torch.empty(n, dtype=torch.uint8, device=dev),
                     torch.empty(n, dtype=torch.int32, device=dev), torch.empty((2, n), dtype=dtype, device=dev))
         self.name = workload_name(n, "fp32" if dtype == torch.float32 else "fp64")
+        if box == "sampler":
+            self.name = self.name.replace("over the table workspace x[0.20,0.60] y[-0.40,0.40] z[0.93,1.40]",
+                                          "over the reference sampler box x[0.33,0.40] y[-0.30,0.11] z[1.05,1.40] (path.py:35-37)")
 
     def launch(self):
         q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out, kernel=self.kernel_choice)
@@ -320,7 +339,7 @@ def run_b200(args):
 
     scaling = "weak"
     if args.config == 2:
-        wl = Config2(torch, solver, args.n, rank, dtype)
+        wl = Config2(torch, solver, args.n, rank, dtype, box=args.box)
     elif args.config == 3:
         wl = Config3(torch, solver, args.n if args.n != N_PER_GPU else 65536, 64, rank, dtype)
     elif args.config == 4:
@@ -481,9 +500,12 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         n_sample = args.cpu_sample or 256 * cores
         rate, threads, secs = cpu_solve_rate(n_sample)
+        np_rate = numpy_solve_rate(3)
         cpu = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
+               "numpy_restatement_solves_per_s_1core": np_rate,
                "sample": f"{n_sample} problems of the same workload ({secs:.1f} s), C oracle (Jacobi-SVD pinv, -O3 "
-                         f"-march=native, OpenMP {threads} threads); the Python+pinocchio reference cannot be installed here"}
+                         f"-march=native, OpenMP {threads} threads); the Python+pinocchio reference cannot be installed "
+                         f"here -- its closest stand-in, the numpy restatement, is timed on 3 problems / 1 core beside it"}
 
     cfg = {"workload": wl.name, "problems_per_gpu_per_step": solves_all / world,
            "l2": "256 MB flush write before every step (inside the timed region)",

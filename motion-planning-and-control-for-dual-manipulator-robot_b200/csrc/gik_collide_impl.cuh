@@ -1,8 +1,8 @@
 // gik_collide_impl.cuh -- collision kernels + their C ABI (included at the end of gik_kernels.cu: one translation
 // unit, one library).  Mapping: ONE CONFIGURATION PER WARP.  The kinematic tree is walked level by level (one joint per lane),
 // the lanes place the geometries (oMg = oMi[parent] * placement, pin.updateGeometryPlacements), then the collision
-// pairs are dealt round-robin to the 32 lanes: bounding-sphere rejection first, boolean GJK on the survivors, one
-// __any_sync per round for the early exit.  The scene (geometries, pair lists) lives in global memory and is read
+// pairs are dealt round-robin to the 32 lanes for the bounding-sphere test, the survivors are compacted into a per-warp
+// list and boolean GJK runs on full warps of candidates, with one __any_sync per round for the early exit.  The scene (geometries, pair lists) lives in global memory and is read
 // through the read-only path; per-configuration traffic is q in (60 B) and one flag out.
 #pragma once
 #include "gik_collide.cuh"
@@ -10,6 +10,7 @@
 namespace gik {
 
 constexpr int kCollideWarps = 4;
+constexpr int kMaxCand = 512;       // per-configuration candidate pairs kept for the narrow phase
 
 template <typename T>
 __global__ void __launch_bounds__(kCollideWarps * 32)
@@ -18,6 +19,7 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
                      uint8_t* __restrict__ out, int invert) {
   __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
   __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
+  __shared__ uint16_t s_cand[kCollideWarps][kMaxCand];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nq = sc->tree.nq, ng = sc->n_geoms;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -61,14 +63,40 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
       }
     }
     __syncwarp();
+    // broad phase over all pairs first (bounding spheres), compacting the survivors into a per-warp list, so that the
+    // narrow phase (GJK, a few hundred instructions, data dependent) runs on FULL warps of candidates instead of on
+    // the one or two lanes of each 32-pair round that happen to survive
     bool hit = false;
-    for (int k0 = 0; k0 < n_pairs; k0 += 32) {
+    int n_cand = 0;
+    for (int k0 = 0; k0 < n_pairs && !hit; k0 += 32) {
       const int k = k0 + lane;
+      bool pass = false;
       if (k < n_pairs) {
         const int a = pa[k], b = pb[k];
-        hit = pair_hits(sc->g[a], &s_oMg[w][a][0], sc->g[b], &s_oMg[w][b][0], margin);
+        const T* Ma = &s_oMg[w][a][0];
+        const T* Mb = &s_oMg[w][b][0];
+        const T dx = Ma[9] - Mb[9], dy = Ma[10] - Mb[10], dz = Ma[11] - Mb[11];
+        const T reach = sc->g[a].bound + sc->g[b].bound + margin;
+        pass = dx * dx + dy * dy + dz * dz <= reach * reach;
       }
-      if (__any_sync(0xffffffffu, hit)) { hit = true; break; }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (n_cand + __popc(m) > kMaxCand) {
+        // list full (never with the reference scene): test this round's survivors in place
+        if (pass) hit = gjk_intersect(make_shape(sc->g[pa[k]], &s_oMg[w][pa[k]][0]), make_shape(sc->g[pb[k]], &s_oMg[w][pb[k]][0]), margin);
+        hit = __any_sync(0xffffffffu, hit);
+      } else {
+        if (pass) s_cand[w][n_cand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+        n_cand += __popc(m);
+      }
+    }
+    __syncwarp();
+    for (int c0 = 0; c0 < n_cand && !hit; c0 += 32) {
+      if (c0 + lane < n_cand) {
+        const int k = s_cand[w][c0 + lane];
+        const int a = pa[k], b = pb[k];
+        hit = gjk_intersect(make_shape(sc->g[a], &s_oMg[w][a][0]), make_shape(sc->g[b], &s_oMg[w][b][0]), margin);
+      }
+      hit = __any_sync(0xffffffffu, hit);
     }
     if (lane == 0) out[i] = (uint8_t)((hit ? 1 : 0) ^ (invert ? 1 : 0));
     __syncwarp();
