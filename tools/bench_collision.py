@@ -32,11 +32,6 @@ def main():
     q0 = torch.zeros((15, n), device=dev)
     q, conv, _, _ = s.solve_soa(q0, pose)
     out = {}
-    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
-        qq, pp = q.to(dt), pose.to(dt)
-        out[f"collision_{name}_Mcfg_s"] = n / timed(lambda: s.collision_soa(qq, pp)) / 1e3
-        out[f"clearance_{name}_Mcfg_s"] = n / timed(lambda: s.clearance_soa(qq, pp, 0.04)) / 1e3
-        out[f"cube_collision_{name}_Mcfg_s"] = n / timed(lambda: s.cube_collision_soa(pp)) / 1e3
     col = s.collision_soa(q, pose).bool()
     out["converged_frac"] = conv.float().mean().item()
     out["colliding_frac_of_converged"] = (col & conv.bool()).float().sum().item() / conv.float().sum().item()
@@ -45,6 +40,11 @@ def main():
     out["solve_ms"] = t_solve
     out["solve_plus_collision_ms"] = t_succ
     out["success_solves_per_s_M"] = n / t_succ / 1e3
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        qq, pp = q.to(dt), pose.to(dt)
+        out[f"collision_{name}_Mcfg_s"] = n / timed(lambda: s.collision_soa(qq, pp)) / 1e3
+        out[f"clearance_{name}_Mcfg_s"] = n / timed(lambda: s.clearance_soa(qq, pp, 0.04)) / 1e3
+        out[f"cube_collision_{name}_Mcfg_s"] = n / timed(lambda: s.cube_collision_soa(pp)) / 1e3
     t0 = time.perf_counter()
     a = (torch.eye(3), torch.tensor([0.33, -0.3, 0.93])); b = (torch.eye(3), torch.tensor([0.4, 0.11, 0.93]))
     import numpy as np
