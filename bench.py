@@ -52,6 +52,8 @@ def parse():
                          "NVLink (falls back to nccl if symmetric memory is unavailable); 'nccl' = all_gather_into_tensor")
     ap.add_argument("--box", default="workspace", choices=["workspace", "sampler"],
                     help="config 2 placement box: the table workspace (default) or the reference sampler's box (path.py:35-37)")
+    ap.add_argument("--early-stop", action="store_true",
+                    help="fast preset GIK_F_EARLY_STOP (NOT the reference's semantics for failed problems; never the default)")
     ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
@@ -211,6 +213,7 @@ class Workload:
     name = ""
     solves = 0
     kernel_choice = None
+    early_stop = False
 
 
 class Config2(Workload):
@@ -228,7 +231,8 @@ class Config2(Workload):
                                           "over the reference sampler box x[0.33,0.40] y[-0.30,0.11] z[1.05,1.40] (path.py:35-37)")
 
     def launch(self):
-        q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out, kernel=self.kernel_choice)
+        q, conv, _, _ = self.solver.solve_soa(self.q0, self.pose, out=self.out, kernel=self.kernel_choice,
+                                              early_stop=self.early_stop)
         return q, conv
 
     def iterations(self):
@@ -351,6 +355,9 @@ def run_b200(args):
         wl.name = f"config5: {total} config-2 problems sharded over {world} GPU(s) + all-gather of q/converged; " + wl.name
         scaling = "strong"
     wl.kernel_choice = args.kernel
+    wl.early_stop = args.early_stop
+    if args.early_stop:
+        wl.name += " [FAST PRESET: early stop of stalled problems -- not the reference's semantics for failed problems]"
     gather = world > 1 and not args.no_gather and args.config in (2, 5)
     if args.config == 5:
         n_total_gather, gather_off = total, lo_i

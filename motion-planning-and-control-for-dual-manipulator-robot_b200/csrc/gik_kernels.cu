@@ -61,6 +61,7 @@ struct SolveArgs {
   int64_t n;
   T eps2, dt, lambda;   // eps2 = eps^2: the predicate compares squared norms
   int32_t max_iters;
+  int32_t early_stop;   // GIK_F_EARLY_STOP: give up on a problem whose squared residual fell < 10 % over 64 iterations
   int32_t lanes;        // problems per warp kept in flight (1..32); < 32 spreads a small batch over more SMs
   unsigned long long* queue;  // work queue head (zeroed on the stream before the launch): next problem to hand out
 };
@@ -100,6 +101,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
   bool active = false;
   bool exhausted = false;   // warp-uniform: the queue has handed out every problem
   int it = 0;
+  T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
   // edge mode state
   int step = 0, nsteps = 0, it_total = 0;
 
@@ -123,6 +125,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           idx = cand;
           active = true;
           it = 0;
+          r_mark = T(3.0e38);
 #pragma unroll
           for (int i = 0; i < kActive; ++i) q[i] = __ldg(a.q_init + (int64_t)tab.act_q[i] * a.q_sc + idx * a.q_si);
           T cube[12];
@@ -154,7 +157,13 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     T dq[kActive], rL, rR;
     ik_iteration<T, true, TZ>(tab, q, tgt, a.lambda, dq, rL, rR);
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
-    const bool done = ok || (it >= a.max_iters);
+    bool stalled = false;
+    if (a.early_stop && (it & 63) == 63) {
+      const T rs = rL + rR;
+      stalled = rs > T(0.9) * r_mark;
+      r_mark = rs;
+    }
+    const bool done = ok || (it >= a.max_iters) || stalled;
 
     if (!done) {
       apply_step(tab, q, dq, a.dt);
@@ -195,6 +204,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         if (ok && step < nsteps) {
           ++step;
           it = 0;
+          r_mark = T(3.0e38);
           T ca[12], cb[12], xi[6], cube[12];
           load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
           load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
@@ -258,6 +268,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
   bool active = false;
   bool exhausted = false;   // warp-uniform: the queue has handed out every problem
   int it = 0;
+  T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
   // edge mode state
   int step = 0, nsteps = 0, it_total = 0;
 
@@ -281,6 +292,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
           idx = cand;
           active = true;
           it = 0;
+          r_mark = T(3.0e38);
           q0 = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
           for (int k = 0; k < 6; ++k)
@@ -314,7 +326,13 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
     F2 dq2[6];
     ik_iteration_packed<TZ>(pt, q0, q2, tgt2, a.lambda, dq0, dq2, rL, rR);
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
-    const bool done = ok || (it >= a.max_iters);
+    bool stalled = false;
+    if (a.early_stop && (it & 63) == 63) {
+      const T rs = rL + rR;
+      stalled = rs > T(0.9) * r_mark;
+      r_mark = rs;
+    }
+    const bool done = ok || (it >= a.max_iters) || stalled;
 
     if (!done) {
       q0 = min_(max_(pt.lo0, q0 + a.dt * dq0), pt.hi0);
@@ -356,6 +374,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         if (ok && step < nsteps) {
           ++step;
           it = 0;
+          r_mark = T(3.0e38);
           T ca[12], cb[12], xi[6], cube[12];
           load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
           load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
@@ -413,6 +432,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   int64_t idx = -1;
   bool active = false, exhausted = false;
   int it = 0, step = 0, nsteps = 0, it_total = 0;
+  T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
 
   for (;;) {
     const unsigned need = exhausted ? 0u : (__ballot_sync(0xffffffffu, enabled && !active) & 0x55555555u);
@@ -429,6 +449,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
           idx = cand;
           active = true;
           it = 0;
+          r_mark = T(3.0e38);
           q[0] = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
           for (int k = 0; k < 6; ++k) q[1 + k] = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * a.q_sc + idx * a.q_si);
@@ -467,7 +488,13 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     hand_phase2(hs, kappa, dqa);
     const T rL = h ? r_o : r, rR = h ? r : r_o;
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
-    const bool done = ok || (it >= a.max_iters);
+    bool stalled = false;
+    if (a.early_stop && (it & 63) == 63) {
+      const T rs = rL + rR;
+      stalled = rs > T(0.9) * r_mark;
+      r_mark = rs;
+    }
+    const bool done = ok || (it >= a.max_iters) || stalled;
 
     if (!done) {
       q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
@@ -505,6 +532,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       } else if (ok && step < nsteps) {
         ++step;
         it = 0;
+        r_mark = T(3.0e38);
         T ca[12], cb[12], xi[6], cube[12];
         load_cube(a.pose, a.pose_sc, a.pose_si, idx, ca);
         load_cube(a.pose_b, a.pose_sc, a.pose_si, idx, cb);
@@ -653,7 +681,7 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
   if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
-      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE)) != 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP)) != 0 ||
       (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
@@ -720,6 +748,7 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   a.dt = (T)prm->dt;
   a.lambda = (T)prm->damping;
   a.max_iters = prm->max_iters;
+  a.early_stop = (prm->flags & GIK_F_EARLY_STOP) ? 1 : 0;
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int blocks = 0, lanes = 32;

@@ -97,10 +97,11 @@ class GraspIK:
     # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL / GIK_F_SCALAR_LANE (fp32: "lane" = packed FFMA2 kernel, "lane1" = scalar)
     _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4, "lane1": 2 | 8}
 
-    def _params(self, eps, dt, max_iters, damping, kernel=None) -> _cabi.GikParams:
+    def _params(self, eps, dt, max_iters, damping, kernel=None, early_stop=False) -> _cabi.GikParams:
         if kernel not in self._KERNEL_FLAGS:
             raise ValueError(f"kernel must be one of {list(self._KERNEL_FLAGS)}")
-        return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), self._KERNEL_FLAGS[kernel])
+        flags = self._KERNEL_FLAGS[kernel] | (16 if early_stop else 0)        # GIK_F_EARLY_STOP
+        return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), flags)
 
     def _chk_dev(self, *ts):
         for t in ts:
@@ -137,10 +138,12 @@ class GraspIK:
         return out
 
     def solve_soa(self, q_init: torch.Tensor, pose: torch.Tensor, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
-                  damping=0.0, out=None, kernel=None):
+                  damping=0.0, out=None, kernel=None, early_stop=False):
         """q_init [nq][n], pose [12][n] (contiguous) -> (q [nq][n], converged u8 [n], iters i32 [n], resid [2][n]).
         `out` may carry preallocated (q, converged, iters, resid) to keep the call allocation-free.
-        `kernel`: None = launcher's choice by batch size, "lane" / "pair" force a thread mapping (same results)."""
+        `kernel`: None = launcher's choice by batch size, "lane" / "pair" force a thread mapping (same results).
+        `early_stop`: fast preset (GIK_F_EARLY_STOP) -- stalled problems are abandoned early; flags and converged q
+        are unchanged, the q / iters of FAILED problems are not the reference's."""
         self._chk_dev(q_init, pose)
         if q_init.dtype != pose.dtype:
             raise TypeError("q_init and pose must share a dtype")
@@ -156,7 +159,7 @@ class GraspIK:
             resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
         else:
             q, conv, iters, resid = out
-        prm = self._params(eps, dt, max_iters, damping, kernel)
+        prm = self._params(eps, dt, max_iters, damping, kernel, early_stop)
         f = getattr(self._lib, f"gik_solve_{_sfx(q_init.dtype)}")
         _cabi.check(f(self._h, n, self._ptr(q_init), self._ptr(pose), ctypes.byref(prm), self._ptr(q),
                       self._ptr(conv), self._ptr(iters), self._ptr(resid), self._stream()), "gik_solve")
@@ -295,7 +298,7 @@ class GraspIK:
         return self.collision_soa(qt.t().contiguous(), cp).bool()
 
     def solve_success_soa(self, q_init, pose, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0, kernel=None,
-                          descend_while_colliding=True):
+                          descend_while_colliding=True, early_stop=False):
         """The reference's FULL success predicate on the device: `success = converged and not collision(q)`
         (inverse_geometry.py:70, 97-98), including its behaviour on converged-but-colliding iterates -- the loop keeps
         descending (the residual keeps shrinking) and re-tests after every update until the configuration is
@@ -307,7 +310,7 @@ class GraspIK:
         -> (q [nq][n], success u8 [n], converged u8 [n], iters i32 [n], resid [2][n])."""
         self._need_scene()
         q, conv, iters, resid = self.solve_soa(q_init, pose, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
-                                               kernel=kernel)
+                                               kernel=kernel, early_stop=early_stop)
         convb = conv.bool()
         # the predicate short-circuits (inverse_geometry.py:70): collision() is only evaluated where both residuals
         # pass, so only the converged columns are tested

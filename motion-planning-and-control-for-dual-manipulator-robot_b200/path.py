@@ -52,10 +52,11 @@ def sample_grasp_poses_batch(robot, n, cubeplacementq0, cubeplacementqgoal, *, q
     p12 = as_pose12(pl, dtype=dtype, device=solver.device)
     pose_soa = p12.t().contiguous()
     if collision == "scene":
-        # a converged-but-colliding sample is rejected either way; the reference's extra descent on it is skipped
+        # a failed sample is rejected either way: the reference's extra descent on converged-but-colliding samples is
+        # skipped and stalled solves are abandoned early (GIK_F_EARLY_STOP); accepted samples are unaffected
         q_soa, succ, _, _, _ = solver.solve_success_soa(qi.unsqueeze(1).expand(solver.nq, n).contiguous(), pose_soa, eps=eps,
                                                         dt=dt, max_iters=max_iters, damping=damping,
-                                                        descend_while_colliding=False)
+                                                        descend_while_colliding=False, early_stop=True)
         ok = succ.bool()
         if min_obstacle_distance is not None and min_obstacle_distance > 0:
             ok &= solver.clearance_soa(q_soa, pose_soa, min_obstacle_distance).bool()

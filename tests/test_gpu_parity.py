@@ -476,3 +476,22 @@ def test_dropin_with_pinocchio_like_objects(table, golden):
     P = np.array([c["cube_R"] + c["cube_p"] for c in golden["cases"]], float)
     qb, ok = gik_b200.computeqgrasppose_batch(robot, np.zeros(15), torch.from_numpy(P), dtype=torch.float64)
     assert ok.all() and np.abs(qb.numpy() - np.array([c["q"] for c in golden["cases"]])).max() < 1e-9
+
+
+def test_early_stop_preset_keeps_flags_and_converged_q(solver):
+    # GIK_F_EARLY_STOP abandons stalled problems; everything the planner uses (flags, q of the successes) is unchanged
+    n = 200000
+    g = torch.Generator(device="cuda:0").manual_seed(12)
+    lo = torch.tensor([0.20, -0.40, 0.93], device="cuda:0"); hi = torch.tensor([0.60, 0.40, 1.40], device="cuda:0")
+    pos = lo + torch.rand((n, 3), device="cuda:0", generator=g) * (hi - lo)
+    pose = torch.cat([torch.eye(3, device="cuda:0").reshape(1, 9).expand(n, 9), pos], 1).t().contiguous()
+    q0 = torch.zeros((15, n), device="cuda:0")
+    for dtype in (torch.float32, torch.float64):
+        a = solver.solve_soa(q0.to(dtype), pose.to(dtype))
+        b = solver.solve_soa(q0.to(dtype), pose.to(dtype), early_stop=True)
+        assert torch.equal(a[1], b[1])                                   # same success flags
+        ok = a[1].bool()
+        assert torch.equal(a[0][:, ok], b[0][:, ok]) and torch.equal(a[2][ok], b[2][ok])
+        assert (b[2][~ok] < 1000).float().mean() > 0.95                  # failures stop early ...
+        assert b[2].sum().item() < 0.85 * a[2].sum().item()              # ... which saves iterations
+        assert (b[2][~ok] >= 127).all() and torch.isfinite(b[0]).all()
