@@ -83,8 +83,9 @@ typedef struct gik_params_s {
 /* NOT the reference semantics for failed problems -- a separately reported fast preset: stop a problem as soon as the
  * sum of its two squared residuals has fallen by less than 10 % over the last 64 iterations (a converging problem
  * shrinks it by 72 % over 64 iterations at dt = 1e-2; a problem pinned at its joint limits plateaus).  The problem is
- * reported non-converged with iters = iterations done and q = the iterate reached.  Success flags and the q of
- * converged problems are unchanged (measured: DESIGN.md). */
+ * reported non-converged with iters = iterations done and q = the iterate reached.  The q of converged problems is
+ * unchanged; success flags agree on 99.9997 % (fp32) / 99.993 % (fp64) of 2^20 workspace problems -- the exceptions
+ * are late convergers (850-1000 iterations) that are given up on; there are no false successes. */
 #define GIK_F_EARLY_STOP 16
 
 typedef struct gik_handle_s* gik_handle_t;
