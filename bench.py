@@ -54,7 +54,7 @@ def parse():
                     help="config 2 placement box: the table workspace (default) or the reference sampler's box (path.py:35-37)")
     ap.add_argument("--early-stop", action="store_true",
                     help="fast preset GIK_F_EARLY_STOP (NOT the reference's semantics for failed problems; never the default)")
-    ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1", "pair1", "pair2"], help="force a thread mapping (default: launcher's choice)")
+    ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1"], help="force a thread mapping (default: launcher's choice)")
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = "f64" if args.config == 3 else "f32"

@@ -79,8 +79,6 @@ typedef struct gik_params_s {
  * per lane) below that.  These force one mapping (A/B measurements, tests). */
 #define GIK_F_LANE_KERNEL 2
 #define GIK_F_PAIR_KERNEL 4
-#define GIK_F_PAIR1_KERNEL 32  /* pair mapping, scalar: one problem per lane pair */
-#define GIK_F_PAIR2_KERNEL 64  /* pair mapping, packed (fp32): two problems per lane pair in f32x2 halves */
 #define GIK_F_SCALAR_LANE 8   /* fp32 lane mapping with scalar FFMA instead of the packed FFMA2 kernel (A/B only) */
 /* NOT the reference semantics for failed problems -- a separately reported fast preset: stop a problem as soon as the
  * sum of its two squared residuals has fallen by less than 10 % over the last 64 iterations (a converging problem

@@ -288,9 +288,8 @@ GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
 // frame; A[:, K] receives the LOCAL Jacobian column of chain joint K ([linear; angular]).  On return (B, b)
 // is hand^-1 in the world.  OFF maps chain joint K >= 1 to its slot in the active-joint arrays.
 // ------------------------------------------------------------------------------------------------------
-// (The constants may be of another type than the state: ArmConst<float> broadcasts into F2 state.)
-template <typename T, int K, int OFF, uint32_t TZ, typename C>
-GIK_HD void chain_step(const ArmConst<C>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
+template <typename T, int K, int OFF, uint32_t TZ>
+GIK_HD void chain_step(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
                        T (&b)[3], T (&A)[6][7]) {
   constexpr int AX = chain_axis(K), I = (AX + 1) % 3, J = (AX + 2) % 3;
   constexpr int SLOT = K == 0 ? 0 : OFF + K;
@@ -316,17 +315,17 @@ GIK_HD void chain_step(const ArmConst<C>& ac, const T (&cs)[kActive], const T (&
     if constexpr (!((TZ >> (3 * K + 1)) & 1u)) b[r] -= B[3 * r + 1] * ac.t[K][1];
     if constexpr (!((TZ >> (3 * K + 2)) & 1u)) b[r] -= B[3 * r + 2] * ac.t[K][2];
   }
-  if constexpr (K > 0) chain_step<T, K - 1, OFF, TZ, C>(ac, cs, sn, B, b, A);
+  if constexpr (K > 0) chain_step<T, K - 1, OFF, TZ>(ac, cs, sn, B, b, A);
 }
 
-template <typename T, int OFF, uint32_t TZ, typename C>
-GIK_HD void hand_chain(const ArmConst<C>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
+template <typename T, int OFF, uint32_t TZ>
+GIK_HD void hand_chain(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9],
                        T (&b)[3], T (&A)[6][7]) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) b[i] = ac.finv_p[i];
-  chain_step<T, 6, OFF, TZ, C>(ac, cs, sn, B, b, A);
+  chain_step<T, 6, OFF, TZ>(ac, cs, sn, B, b, A);
 }
 
 // hook target of one hand: cube * hook offset (tools.getcubeplacement, tools.py:54-59)
@@ -392,11 +391,11 @@ struct HandState {
   T yf[6], zf[6];
 };
 
-template <typename T, int OFF, uint32_t TZ, typename C>
-GIK_HD void hand_phase1(const ArmConst<C>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
+template <typename T, int OFF, uint32_t TZ>
+GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
                         T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
   T B[9], b[3], A[6][7], e[6];
-  hand_chain<T, OFF, TZ, C>(ac, cs, sn, B, b, A);
+  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
   hand_error(B, b, tgt, e);
   resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
 
@@ -536,14 +535,14 @@ GIK_HD void fk_frames(const DevTable<T>& tab, const T (&q)[kActive], T (&frames)
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   T B[9], b[3], A[6][7];
-  hand_chain<T, 0, 0, T>(tab.arm[0], cs, sn, B, b, A);
+  hand_chain<T, 0, 0>(tab.arm[0], cs, sn, B, b, A);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {  // invert: R = B^T, p = -B^T b
 #pragma unroll
     for (int c = 0; c < 3; ++c) frames[0][3 * r + c] = B[3 * c + r];
     frames[0][9 + r] = -(B[r] * b[0] + B[3 + r] * b[1] + B[6 + r] * b[2]);
   }
-  hand_chain<T, 6, 0, T>(tab.arm[1], cs, sn, B, b, A);
+  hand_chain<T, 6, 0>(tab.arm[1], cs, sn, B, b, A);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -558,8 +557,8 @@ GIK_HD void frame_jacobians(const DevTable<T>& tab, const T (&q)[kActive], T (&A
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   T B[9], b[3];
-  hand_chain<T, 0, 0, T>(tab.arm[0], cs, sn, B, b, AL);
-  hand_chain<T, 6, 0, T>(tab.arm[1], cs, sn, B, b, AR);
+  hand_chain<T, 0, 0>(tab.arm[0], cs, sn, B, b, AL);
+  hand_chain<T, 6, 0>(tab.arm[1], cs, sn, B, b, AR);
 }
 
 }  // namespace gik

@@ -547,193 +547,6 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   }
 }
 
-// ========================================================================================================
-// Pair kernel, packed (fp32): one HAND per lane as in the pair kernel, and TWO PROBLEMS per lane pair carried in the
-// halves of F2 registers, so one warp instruction stream (FFMA2 / FMUL2) advances up to 32 problems instead of 16.
-// For the batches that cannot fill the machine (path.py edge projection: 4096 chains) the cost is issue slots per
-// chain-iteration, and this halves it again.  Each half ("slot") is an independent problem with its own queue
-// refill, iteration count and edge-march state; the arm constants broadcast into both halves.
-// ========================================================================================================
-#ifndef GIK_MINB_PAIR2
-#define GIK_MINB_PAIR2 2
-#endif
-__device__ __forceinline__ float& half_of(F2& v, int s) { return s ? v.y : v.x; }
-__device__ __forceinline__ float half_of(const F2& v, int s) { return s ? v.y : v.x; }
-
-template <int MODE, uint32_t TZ>
-__global__ void __launch_bounds__(GIK_THREADS, GIK_MINB_PAIR2)
-gik_solve_pair2_kernel(const __grid_constant__ DevTable<float> tab, const __grid_constant__ SolveArgs<float> a) {
-  using T = float;
-  const int lane = threadIdx.x & 31;
-  const int h = lane & 1;
-  const int off = 1 + 6 * h;
-  const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
-  const int64_t n = a.n;
-  const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = lane pairs per warp (1..16), two problems each
-  const ArmConst<T>& ac = tab.arm[h];
-
-  F2 q[7], tgt[12];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) q[i] = F2(0.0f);
-#pragma unroll
-  for (int c = 0; c < 12; ++c) tgt[c] = F2((c % 4 == 0 && c < 9) ? 1.0f : 0.0f);
-
-  int64_t idx[2] = {-1, -1};
-  bool active[2] = {false, false};
-  bool exhausted = false;
-  int it[2] = {0, 0}, step[2] = {0, 0}, nsteps[2] = {0, 0}, it_total[2] = {0, 0};
-  T r_mark[2] = {T(3.0e38), T(3.0e38)};
-
-  auto set_target = [&](int s, const T (&cube)[12]) {
-    T t[12];
-    hook_target(ac, cube, t);
-#pragma unroll
-    for (int c = 0; c < 12; ++c) half_of(tgt[c], s) = t[c];
-  };
-
-  for (;;) {
-    // ---------------- refill, slot by slot ----------------
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const unsigned need = exhausted ? 0u : (__ballot_sync(0xffffffffu, enabled && !active[s]) & 0x55555555u);
-      if (need) {
-        const int leader = __ffs(need) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
-        wait_resident(a, base + __popc(need));
-        if (enabled && !active[s]) {
-          const int64_t cand = (int64_t)base + __popc(need & lower_pairs);
-          if (cand < n) {
-            idx[s] = cand;
-            active[s] = true;
-            it[s] = 0;
-            r_mark[s] = T(3.0e38);
-            half_of(q[0], s) = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + cand * a.q_si);
-#pragma unroll
-            for (int k = 0; k < 6; ++k)
-              half_of(q[1 + k], s) = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * a.q_sc + cand * a.q_si);
-            T cube[12];
-            load_cube(a.pose, a.pose_sc, a.pose_si, cand, cube);
-            if (MODE == MODE_EDGES) {
-              nsteps[s] = __ldg(a.num_steps + cand);
-              step[s] = 1;
-              it_total[s] = 0;
-              T cb[12], xi[6], ca[12];
-#pragma unroll
-              for (int c = 0; c < 12; ++c) ca[c] = cube[c];
-              load_cube(a.pose_b, a.pose_sc, a.pose_si, cand, cb);
-              se3_delta(ca, cb, xi);
-              se3_advance(ca, xi, T(1) / T(nsteps[s]), cube);
-              if (nsteps[s] < 1) {
-                if (h == 0) { a.n_valid[cand] = 0; if (a.iters) a.iters[cand] = 0; }
-                active[s] = false;
-              }
-            }
-            set_target(s, cube);
-          }
-        }
-      }
-    }
-    if (exhausted && !__any_sync(0xffffffffu, active[0] || active[1])) break;
-
-    // ---------------- one descent iteration: this lane's hand, both slots ----------------
-    F2 cs[kActive], sn[kActive], Sy, Sz, r, dqa[6];
-    HandState<F2> hs;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      float s0, c0, s1, c1;
-      sincos_<true>(q[i].x, s0, c0);
-      sincos_<true>(q[i].y, s1, c1);
-      cs[i] = F2(c0, c1); sn[i] = F2(s0, s1);
-    }
-    hand_phase1<F2, 0, TZ>(ac, cs, sn, tgt, F2(a.lambda), hs, Sy, Sz, r);
-    F2 Sy_o, Sz_o, r_o;
-    Sy_o.x = __shfl_xor_sync(0xffffffffu, Sy.x, 1); Sy_o.y = __shfl_xor_sync(0xffffffffu, Sy.y, 1);
-    Sz_o.x = __shfl_xor_sync(0xffffffffu, Sz.x, 1); Sz_o.y = __shfl_xor_sync(0xffffffffu, Sz.y, 1);
-    r_o.x = __shfl_xor_sync(0xffffffffu, r.x, 1); r_o.y = __shfl_xor_sync(0xffffffffu, r.y, 1);
-    F2 kappa;
-    kappa.x = h ? chest_rate(Sy_o.x, Sz_o.x, Sy.x, Sz.x) : chest_rate(Sy.x, Sz.x, Sy_o.x, Sz_o.x);
-    kappa.y = h ? chest_rate(Sy_o.y, Sz_o.y, Sy.y, Sz.y) : chest_rate(Sy.y, Sz.y, Sy_o.y, Sz_o.y);
-    hand_phase2(hs, kappa, dqa);
-
-    bool ok[2], done[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const T rL = h ? half_of(r_o, s) : half_of(r, s), rR = h ? half_of(r, s) : half_of(r_o, s);
-      ok[s] = (rL < a.eps2) && (rR < a.eps2) && (it[s] < a.max_iters);
-      bool stalled = false;
-      if (a.early_stop && (it[s] & 63) == 63) {
-        const T rs = rL + rR;
-        stalled = rs > T(0.9) * r_mark[s];
-        r_mark[s] = rs;
-      }
-      done[s] = ok[s] || (it[s] >= a.max_iters) || stalled;
-    }
-    // update (both halves computed; a finished slot's half is not committed)
-    {
-      const F2 dt2 = F2(a.dt);
-      F2 qn[7];
-      qn[0] = min_(max_(F2(tab.lo[0]), q[0] + dt2 * kappa), F2(tab.hi[0]));
-#pragma unroll
-      for (int k = 0; k < 6; ++k) qn[1 + k] = min_(max_(F2(tab.lo[off + k]), q[1 + k] + dt2 * dqa[k]), F2(tab.hi[off + k]));
-#pragma unroll
-      for (int s = 0; s < 2; ++s)
-        if (!done[s]) {
-#pragma unroll
-          for (int i = 0; i < 7; ++i) half_of(q[i], s) = half_of(qn[i], s);
-          ++it[s];
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (!(done[s] && active[s])) continue;
-      const bool batch = (MODE == MODE_BATCH);
-      const int64_t id = idx[s];
-      if (!batch) it_total[s] += it[s];
-      if (batch || ok[s]) {
-        const bool moved = batch ? (it[s] > 0) : (it_total[s] > 0);
-        const int n_dst = batch ? a.n_dst : 1;
-        const int64_t ld = batch ? a.out_sc : n, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + id : id;
-        for (int d = 0; d < n_dst; ++d) {
-          T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step[s] - 1) * tab.nq * n;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col * cs_] = half_of(q[1 + k], s);
-          if (h == 0) {
-            dst[(int64_t)tab.act_q[0] * ld + col * cs_] = half_of(q[0], s);
-            for (int p = 0; p < tab.n_passive; ++p) {
-              const int j = tab.passive_q[p];
-              T v = __ldg(a.q_init + (int64_t)j * a.q_sc + id * a.q_si);
-              if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
-              dst[(int64_t)j * ld + col * cs_] = v;
-            }
-            if (batch) a.conv_dst[d][col] = ok[s] ? 1 : 0;
-          }
-        }
-      }
-      if (batch) {
-        if (h == 0 && a.iters) a.iters[id] = it[s];
-        if (a.resid) a.resid[(int64_t)h * a.res_sc + id * a.res_si] = sqrt_(half_of(r, s));
-        active[s] = false;
-      } else if (ok[s] && step[s] < nsteps[s]) {
-        ++step[s];
-        it[s] = 0;
-        r_mark[s] = T(3.0e38);
-        T ca[12], cb[12], xi[6], cube[12];
-        load_cube(a.pose, a.pose_sc, a.pose_si, id, ca);
-        load_cube(a.pose_b, a.pose_sc, a.pose_si, id, cb);
-        se3_delta(ca, cb, xi);
-        se3_advance(ca, xi, T(step[s]) / T(nsteps[s]), cube);
-        set_target(s, cube);
-      } else {
-        if (h == 0) { a.n_valid[id] = ok[s] ? step[s] : step[s] - 1; if (a.iters) a.iters[id] = it_total[s]; }
-        active[s] = false;
-      }
-    }
-  }
-}
-
 // ---------------- K1 / K2: forward kinematics and LOCAL frame Jacobians (parity entries) ----------------
 template <typename T>
 __global__ void __launch_bounds__(128) gik_fk_kernel(const __grid_constant__ DevTable<T> tab, int64_t n,
@@ -868,8 +681,7 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
   if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
-      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP | GIK_F_PAIR1_KERNEL |
-                    GIK_F_PAIR2_KERNEL)) != 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP)) != 0 ||
       (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
@@ -913,7 +725,7 @@ int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* b
 // is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
 // params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
 template <typename T, int MODE>
-int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair, bool* pair2) {
+int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair) {
   int64_t max_warps = 0;
   int rc;
   if constexpr (sizeof(T) == 4) {
@@ -925,19 +737,8 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_wa
   if (rc) return rc;
   *pair = sizeof(T) == 8 || n <= 16 * max_warps;
   if (flags & GIK_F_LANE_KERNEL) *pair = false;
-  if (flags & (GIK_F_PAIR_KERNEL | GIK_F_PAIR1_KERNEL | GIK_F_PAIR2_KERNEL)) *pair = true;
-  *pair2 = false;
-  if (*pair) {
-    rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, &max_warps);
-    if (rc) return rc;
-    if constexpr (sizeof(T) == 4) {
-      // packed pair kernel (two problems per lane pair) once even the pair kernel leaves half of its pairs empty
-      if ((n <= 8 * max_warps || (flags & GIK_F_PAIR2_KERNEL)) && !(flags & GIK_F_PAIR1_KERNEL)) {
-        *pair2 = true;
-        rc = grid_dims(h, gik_solve_pair2_kernel<MODE, 0>, (n + 1) / 2, 16, blocks, per_warp, nullptr);
-      }
-    }
-  }
+  if (flags & GIK_F_PAIR_KERNEL) *pair = true;
+  if (*pair) rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
   return rc;
 }
 
@@ -951,8 +752,8 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int blocks = 0, lanes = 32;
-  bool pair = false, pair2 = false;
-  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair, &pair2);
+  bool pair = false;
+  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair);
   if (rc) return rc;
   a.lanes = lanes;
   a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
@@ -961,12 +762,7 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   const DevTable<T>& tab = table_of<T>(h);
   const bool nx = (tab.tzero & kNextageTZ) == kNextageTZ;   // table has (at least) the Nextage zero pattern: skip those FMAs
   cudaStream_t st = (cudaStream_t)stream;
-  if (pair2) {
-    if constexpr (sizeof(T) == 4) {
-      if (nx) gik_solve_pair2_kernel<MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
-      else gik_solve_pair2_kernel<MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
-    }
-  } else if (pair) {
+  if (pair) {
     if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
   } else if constexpr (sizeof(T) == 4) {
@@ -1258,9 +1054,9 @@ int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blo
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int b = 0, l = 32, rc;
-  bool pair = false, pair2 = false;
-  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, 0, &b, &l, &pair, &pair2);
-  else if (elem_size == 8) rc = choose_launch<double, MODE_BATCH>(h, n, 0, &b, &l, &pair, &pair2);
+  bool pair = false;
+  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, 0, &b, &l, &pair);
+  else if (elem_size == 8) rc = choose_launch<double, MODE_BATCH>(h, n, 0, &b, &l, &pair);
   else return GIK_E_PARAM;
   if (rc) return rc;
   *blocks = b; *threads = GIK_THREADS;

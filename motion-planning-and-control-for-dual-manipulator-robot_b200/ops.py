@@ -95,8 +95,7 @@ class GraspIK:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL / GIK_F_SCALAR_LANE (fp32: "lane" = packed FFMA2 kernel, "lane1" = scalar)
-    # "pair" = pair mapping, launcher picks scalar / packed; "pair1" / "pair2" force one of them
-    _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4, "lane1": 2 | 8, "pair1": 32, "pair2": 64}
+    _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4, "lane1": 2 | 8}
 
     def _params(self, eps, dt, max_iters, damping, kernel=None, early_stop=False) -> _cabi.GikParams:
         if kernel not in self._KERNEL_FLAGS:

@@ -211,17 +211,16 @@ def test_pair_kernel_equals_lane_kernel(solver, dtype):
     n = 3001
     P = _t(make_poses(n, 61), dtype).t().contiguous()
     q0 = torch.zeros((15, n), dtype=dtype, device="cuda:0")
-    # fp64: lane and pair kernels run the same operations on the same values -> bit-identical.  fp32: "lane" / "pair2" are
-    # the packed FFMA2 kernels (two hands, resp. two problems, in one F2 register) and "lane1" / "pair1" their scalar
-    # forms; the compiler contracts multiplies and adds into FMAs differently in the four kernels, so they agree at
-    # round-off level (flags, iterations, q)
+    # fp64: lane and pair kernels run the same operations on the same values -> bit-identical.  fp32: "lane" is the
+    # packed FFMA2 kernel (both hands in one F2 register) and "lane1" its scalar form; the compiler contracts multiplies
+    # and adds into FMAs differently in the three kernels, so they agree at round-off level (flags, iterations, q)
     b = solver.solve_soa(q0, P, kernel="pair")
     if dtype == torch.float64:
         a = solver.solve_soa(q0, P, kernel="lane")
         assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
         assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
     else:
-        for kern in ("lane", "lane1", "pair1", "pair2"):
+        for kern in ("lane", "lane1"):
             p = solver.solve_soa(q0, P, kernel=kern)
             assert (p[1] == b[1]).float().mean() >= 0.999
             both = (p[1] & b[1]).bool()
@@ -252,7 +251,7 @@ def test_scatter_entry_on_one_gpu(solver):
     n, n_total, off = 1000, 2500, 700
     P = _t(make_poses(n, 71), torch.float32).t().contiguous()
     q0 = torch.zeros((15, n), dtype=torch.float32, device="cuda:0")
-    for kern in ("lane", "lane1", "pair1", "pair2"):
+    for kern in ("lane", "lane1", "pair"):
         ref = solver.solve_soa(q0, P, kernel=kern)
         qa = [torch.full((15, n_total), -7.0, device="cuda:0") for _ in range(2)]
         ca = [torch.full((n_total,), 9, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
