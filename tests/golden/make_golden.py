@@ -7,6 +7,8 @@
                          pinned there by the SLSQP equality constraints of control.py:110-119 and produced at
                          control.py:435-436; plus the notebook known answers (lab_instructions.ipynb:210-226,
                          252, 290-293) typed from the recorded cell outputs.
+  trajectory2_reference.json -- trajectory2.json as saved by control.save_trajectory_to_json (control.py:203-216):
+                         the control points of a maketraj result and of its two derivative curves.
   nextage_table.json  -- the kinematic table flattened from the reference's URDFs
                          (models/nextagea_description/urdf/NextageaOpen.urdf, models/cubes/cube_small.urdf)
                          with ROBOT_PLACEMENT (config.py:33) applied as in setup_pinocchio.py:28-32.
@@ -43,11 +45,17 @@ def main(ref):
         },
     }
     json.dump(gold, open(os.path.join(HERE, "ik_golden.json"), "w"), indent=1)
+    json.dump(t2, open(os.path.join(HERE, "trajectory2_reference.json"), "w"))     # the reference's saved maketraj result
     import gik_b200
     tab = gik_b200.from_urdf(os.path.join(ref, "models/nextagea_description/urdf/NextageaOpen.urdf"),
                              os.path.join(ref, "models/cubes/cube_small.urdf"))
     json.dump(tab.to_json(), open(os.path.join(HERE, "nextage_table.json"), "w"), indent=1)
-    print("wrote ik_golden.json, nextage_table.json")
+    from gik_b200 import scene
+    os.makedirs(os.path.join(HERE, "..", "..", "motion-planning-and-control-for-dual-manipulator-robot_b200", "data"), exist_ok=True)
+    json.dump(scene.reference_scene_from(ref).to_json(),
+              open(os.path.join(HERE, "..", "..", "motion-planning-and-control-for-dual-manipulator-robot_b200", "data",
+                                "nextage_scene.json"), "w"))
+    print("wrote ik_golden.json, trajectory2_reference.json, nextage_table.json, data/nextage_scene.json")
 
 
 if __name__ == "__main__":
