@@ -81,11 +81,14 @@ def edge_num_steps(cube_a12: torch.Tensor, cube_b12: torch.Tensor, step_size=STE
 
 def project_edges_batch(robot, q_start, cube_a, cube_b, *, num_steps=None, step_size=STEP_SIZE, max_steps=None,
                         dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
-                        return_info=False):
+                        return_info=False, scene_tests=False):
     """E edges marched at once.  q_start [E,nq]; cube_a / cube_b [E,12|4x4|7|3]; num_steps int [E] (default from
     `step_size` as in the reference).  Returns (q_path [E,S,nq], n_valid int32 [E]) where q_path[e, k] is the
     configuration for placement Interpolate(a, b, (k+1)/num_steps[e]) and n_valid[e] counts the steps before the
-    first failure (path.py:153-156); entries beyond n_valid are zero."""
+    first failure (path.py:153-156); entries beyond n_valid are zero.  `scene_tests=True` also applies, for every edge at
+    once, the two collision tests of the reference loop -- the cube against the table / obstacle at each interpolated
+    placement (path.py:144-149) and the robot collision term of the grasp predicate -- and cuts each edge at its first
+    failing step."""
     solver = solver_for(robot)
     dev = solver.device
     a12 = as_pose12(cube_a, dtype=dtype, device=dev)
@@ -105,10 +108,34 @@ def project_edges_batch(robot, q_start, cube_a, cube_b, *, num_steps=None, step_
     path, nv, itt = solver.project_edges_soa(qs.t().contiguous(), a12.t().contiguous(), b12.t().contiguous(),
                                              ns.contiguous(), max_steps, eps=eps, dt=dt, max_iters=max_iters,
                                              damping=damping)
+    if scene_tests and E and max_steps:
+        nv = _cut_at_first_collision(solver, path, nv, a12, b12, ns, max_steps)
     out = (path.permute(2, 0, 1), nv)
     if return_info:
         out = out + (itt,)
     return out
+
+
+def _cut_at_first_collision(solver, path, nv, a12, b12, ns, S):
+    """path [S][nq][E] (zero beyond n_valid), nv [E] -> nv cut at the first step whose cube placement or robot
+    configuration collides with the attached scene; rows beyond the new nv are zeroed."""
+    solver._need_scene()
+    E = a12.shape[0]
+    dev = a12.device
+    k = torch.arange(S, device=dev)
+    valid = k[None, :] < nv[:, None]                                            # [E,S]
+    e_idx, k_idx = torch.nonzero(valid, as_tuple=True)
+    bad = torch.zeros((E, S), dtype=torch.bool, device=dev)
+    if e_idx.numel():
+        alpha = (k_idx + 1).to(a12.dtype) / ns[e_idx].to(a12.dtype)
+        poses = se3_interpolate(a12[e_idx], b12[e_idx], alpha).t().contiguous()   # [12][M]
+        q = path[k_idx, :, e_idx].t().contiguous()                                # [nq][M]
+        hit = solver.cube_collision_soa(poses).bool() | solver.collision_soa(q, poses).bool()
+        bad[e_idx, k_idx] = hit
+    first_bad = torch.where(bad.any(dim=1), bad.to(torch.int32).argmax(dim=1), torch.full((E,), S, device=dev)).to(nv.dtype)
+    nv_new = torch.minimum(nv, first_bad)
+    path.mul_((k[None, :] < nv_new[:, None]).t()[:, None, :].to(path.dtype))      # zero the rows that were cut
+    return nv_new
 
 
 def project_path(robot, cube, q_curr, cube_curr, cube_rand, step_size=STEP_SIZE, viz=None, *, cube_collision=None,
@@ -257,9 +284,11 @@ def _like(template, pose12):
     return pose12
 
 
-def se3_interpolate(a12: torch.Tensor, b12: torch.Tensor, alpha: float) -> torch.Tensor:
-    """pin.SE3.Interpolate(A, B, alpha) = A exp6(alpha log6(A^-1 B)) on [B,12] float64 host/device tensors
-    (bookkeeping for `project_path`'s returned cube_path; the kernel has its own copy in gik_core.cuh)."""
+def se3_interpolate(a12: torch.Tensor, b12: torch.Tensor, alpha) -> torch.Tensor:
+    """pin.SE3.Interpolate(A, B, alpha) = A exp6(alpha log6(A^-1 B)) on [B,12] host/device tensors; alpha a float or a
+    [B] tensor (bookkeeping for the returned cube paths and the scene tests; the kernel has its own copy in
+    gik_core.cuh)."""
+    alpha = torch.as_tensor(alpha, dtype=a12.dtype, device=a12.device).reshape(-1, 1)
     Ra, pa = a12[:, :9].reshape(-1, 3, 3), a12[:, 9:]
     Rb, pb = b12[:, :9].reshape(-1, 3, 3), b12[:, 9:]
     R = Ra.transpose(1, 2) @ Rb

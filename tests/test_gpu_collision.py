@@ -182,3 +182,26 @@ def test_success_rate_experiment_matches_oracle(solver, table_c, scene_c, c_orac
     P = P[free][:48]
     _, ok, _ = c_oracle.solve_success(table_c, scene_c, np.zeros((len(P), 15)), P)
     assert abs(100.0 * ok.mean() - res[0][1]) < 1e-9
+
+
+def test_project_edges_batch_scene_tests_match_single_edge_dropin(solver, golden):
+    # batched cut-at-first-collision == the per-edge drop-in project_path with the scene tests
+    import gik_b200
+    rng = np.random.default_rng(8)
+    q0 = np.array(golden["cases"][0]["q"])
+    a = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0.33, -0.3, 0.93], float)
+    E = 12
+    B = np.tile(a, (E, 1)); B[:, 9:] = rng.uniform([0.3, -0.3, 0.9], [0.5, 0.1, 1.3], size=(E, 3))
+    B[0, 9:] = [0.43, -0.1, 0.95]                                    # straight into the obstacle
+    A = np.tile(a, (E, 1)); Q0 = np.tile(q0, (E, 1))
+    path, nv = gik_b200.project_edges_batch(solver, torch.from_numpy(Q0).cuda(), torch.from_numpy(A).cuda(),
+                                            torch.from_numpy(B).cuda(), dtype=torch.float64, scene_tests=True)
+    path0, nv0 = gik_b200.project_edges_batch(solver, torch.from_numpy(Q0).cuda(), torch.from_numpy(A).cuda(),
+                                              torch.from_numpy(B).cuda(), dtype=torch.float64)
+    assert (nv <= nv0).all() and (nv < nv0).any()                    # some edge is cut by a collision
+    for e in range(E):
+        rp, cp = gik_b200.project_path(solver, None, q0, A[e], B[e], cube_collision="scene", collision="scene")
+        assert len(rp) - 1 == int(nv[e])
+        for k in range(int(nv[e])):
+            assert np.abs(rp[k + 1] - path[e, k].cpu().numpy()).max() < 1e-12
+        assert path[e, int(nv[e]):].abs().max().item() == 0 if int(nv[e]) < path.shape[1] else True
