@@ -505,7 +505,7 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1 and args.config == 2:
         cores = os.cpu_count() or 1
-        n_sample = args.cpu_sample or 256 * cores
+        n_sample = args.cpu_sample or 512 * cores
         rate, threads, secs = cpu_solve_rate(n_sample)
         np_rate = numpy_solve_rate(3)
         cpu = {"value": rate, "unit": "solves/s", "cores": threads, "kind": "port",
