@@ -23,7 +23,7 @@ import weakref
 import numpy as np
 import torch
 
-from .model import KinematicTable, from_pinocchio, nextage_table
+from .model import KinematicTable, from_pinocchio
 from .ops import DT, EPSILON, MAX_ITERS, GraspIK, as_pose12, default_solver
 
 _solvers = weakref.WeakKeyDictionary()

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .inverse_geometry import _pose_to_array, solver_for
-from .ops import DT, EPSILON, MAX_ITERS, GraspIK, as_pose12
+from .ops import DT, EPSILON, MAX_ITERS, as_pose12
 
 Z_MIN, Z_MAX = 1.05, 1.4          # path.py:37
 STEP_SIZE = 0.025                 # path.py:125, 203-206
