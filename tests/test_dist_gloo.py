@@ -37,7 +37,7 @@ def _worker(rank, world, port, n_total, out):
 @pytest.mark.parametrize("n_total", [64, 37])          # even split, and ragged slabs that need padding
 def test_all_gather_results_world2(n_total):
     world = 2
-    with mp.Manager() as m:
+    with mp.get_context("spawn").Manager() as m:
         out = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), n_total, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
