@@ -51,3 +51,47 @@ def grasp_success_rate(robot, cubeplacementq0, cubeplacementqgoal, std_devs=STD_
         _, succ, _, _, _ = solver.solve_success_soa(q0, P.t().contiguous(), descend_while_colliding=descend_while_colliding)
         out.append((tuple(sd), 100.0 * float(succ.double().mean().item()), int(P.shape[0])))
     return out
+
+
+def _random_endpoint(solver, a, b, sd, dtype, generator, batch=256):
+    """path_TESTS.sample_random_cube_placement: a clipped-Gaussian cube placement with a valid, collision-free grasp
+    configuration that keeps the 0.04 m clearance (the same acceptance rule as path.sample_cube_placement)."""
+    while True:
+        pl = sample_gaussian_placements(batch, a, b, sd, device=solver.device, dtype=dtype, generator=generator)
+        p12 = as_pose12(pl, dtype=dtype, device=solver.device).t().contiguous()
+        q0 = torch.zeros((solver.nq, batch), dtype=dtype, device=solver.device)
+        q, succ, _, _, _ = solver.solve_success_soa(q0, p12, descend_while_colliding=False, early_stop=True)
+        ok = succ.bool() & ~solver.cube_collision_soa(p12).bool() & solver.clearance_soa(q, p12, 0.04).bool()
+        idx = torch.nonzero(ok).flatten()
+        if idx.numel():
+            i = int(idx[0])
+            return q[:, i].double().cpu().numpy(), (np.eye(3), pl[i].double().cpu().numpy())
+
+
+def rrt_connect_trials(robot, cubeplacementq0, cubeplacementqgoal, std_devs=STD_DEVS[:4], trials=100, *,
+                       dtype=torch.float64, generator=None, rng=None):
+    """The reference's planner experiment (path_TESTS.py:910-990): for each spread, `trials` planning queries between
+    two random valid cube placements; success rate, wall time and RRT iteration statistics per spread."""
+    import time
+    from .path import computepath
+    solver = solver_for(robot)
+    solver._need_scene()
+    rng = rng if rng is not None else np.random.default_rng()
+    results = []
+    for sd in std_devs:
+        times, iters, wins = [], [], 0
+        for _ in range(trials):
+            q_init, c0 = _random_endpoint(solver, cubeplacementq0, cubeplacementqgoal, sd, dtype, generator)
+            q_goal, c1 = _random_endpoint(solver, cubeplacementq0, cubeplacementqgoal, sd, dtype, generator)
+            t0 = time.perf_counter()
+            path, stats = computepath(q_init, q_goal, c0, c1, robot=solver, rng=rng, generator=generator, dtype=dtype,
+                                      return_stats=True)
+            times.append(time.perf_counter() - t0)
+            iters.append(stats["iterations"])
+            wins += bool(path)
+        results.append({"std_dev": tuple(sd), "success_rate": 100.0 * wins / trials,
+                        "avg_time": float(np.mean(times)), "max_time": float(np.max(times)), "min_time": float(np.min(times)),
+                        "std_time": float(np.std(times)), "avg_iterations": float(np.mean(iters)),
+                        "max_iterations": int(np.max(iters)), "min_iterations": int(np.min(iters)),
+                        "std_iterations": float(np.std(iters))})
+    return results

@@ -205,3 +205,14 @@ def test_project_edges_batch_scene_tests_match_single_edge_dropin(solver, golden
         for k in range(int(nv[e])):
             assert np.abs(rp[k + 1] - path[e, k].cpu().numpy()).max() < 1e-12
         assert path[e, int(nv[e]):].abs().max().item() == 0 if int(nv[e]) < path.shape[1] else True
+
+
+def test_planner_trials_experiment(solver):
+    # path_TESTS.py:910-990 in small: random start / goal placements, planning statistics
+    from gik_b200 import experiments
+    a = (np.eye(3), np.array([0.33, -0.3, 0.93])); b = (np.eye(3), np.array([0.4, 0.11, 0.93]))
+    res = experiments.rrt_connect_trials(solver, a, b, std_devs=[(0.1, 0.1, 0.1)], trials=3,
+                                         generator=torch.Generator(device="cuda:0").manual_seed(4), rng=np.random.default_rng(4))
+    r = res[0]
+    assert r["std_dev"] == (0.1, 0.1, 0.1) and 0.0 <= r["success_rate"] <= 100.0
+    assert r["success_rate"] >= 66.0 and r["min_iterations"] >= 1 and r["avg_time"] < 30.0
