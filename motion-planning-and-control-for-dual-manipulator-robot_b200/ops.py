@@ -242,7 +242,11 @@ class GraspIK:
         return self
 
     def _need_scene(self):
+        """Attach the packaged reference scene on first use -- only for the reference's own robot; any other table
+        needs an explicit attach_scene(scene) (a silently wrong collision model is worse than an error)."""
         if getattr(self, "scene", None) is None:
+            if self.table.meta.get("source") not in ("builtin-nextage", "urdf", "pinocchio"):
+                raise RuntimeError("no collision scene attached: call GraspIK.attach_scene(scene) for this robot")
             self.attach_scene()
 
     def collision_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None) -> torch.Tensor:
