@@ -34,6 +34,25 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(GikTable) == 264 + 8 * 32 * (9 + 3 + 1 + 1) + 8 + 8 * 2 * (9 + 3 + 9 + 3)
 
 
+def test_struct_sizes_match_the_c_header(tmp_path):
+    # compile sizeof() of every ABI struct from include/gik.h with the C compiler and compare with the ctypes mirrors
+    import shutil
+    import subprocess
+    from gik_b200 import _cabi
+    from gik_b200.model import GikTable
+    from gik_b200.scene import GikGeom, GikScene
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "gik.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(gik_table_t), '
+                   'sizeof(gik_params_t), sizeof(gik_geom_t), sizeof(gik_scene_t));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(GikTable), ctypes.sizeof(_cabi.GikParams), ctypes.sizeof(GikGeom), ctypes.sizeof(GikScene)]
+
+
 def test_error_paths_without_gpu():
     from gik_b200 import _cabi
     lib = _cabi.lib()
