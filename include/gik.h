@@ -217,6 +217,14 @@ int gik_scene_attach(gik_handle_t h, const gik_scene_t* scene);
 int gik_collision_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, uint8_t* colliding, void* stream);
 int gik_collision_f64(gik_handle_t h, int64_t n, const double* q, const double* cube_pose, uint8_t* colliding, void* stream);
 
+/* Same test on a SUBSET of the columns: sel [n_sel] (device, int64) lists the columns of the [.][n] arrays to test;
+ * colliding[sel[k]] is written, the other entries are left untouched.  This is the predicate's short-circuit
+ * (inverse_geometry.py:70 evaluates collision() only where both residuals pass) without gathering the columns. */
+int gik_collision_sel_f32(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const float* q,
+                          const float* cube_pose, uint8_t* colliding, void* stream);
+int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const double* q,
+                          const double* cube_pose, uint8_t* colliding, void* stream);
+
 /* Replaces `distanceToObstacle(robot, q) >= threshold` (tools.py:38-51 with path.py:61-62): clear [n] = 1 when every
  * pair whose second geometry is the table or the obstacle is at least `threshold` apart. */
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, double threshold, uint8_t* clear, void* stream);

@@ -16,14 +16,17 @@ template <typename T>
 __global__ void __launch_bounds__(kCollideWarps * 32)
 gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pb,
                      int n_pairs, int64_t n, const T* __restrict__ q, const T* __restrict__ cube_pose, T margin,
-                     uint8_t* __restrict__ out, int invert) {
+                     uint8_t* __restrict__ out, int invert, const int64_t* __restrict__ sel, int64_t n_sel) {
   __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
   __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
   __shared__ uint16_t s_cand[kCollideWarps][kMaxCand];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nq = sc->tree.nq, ng = sc->n_geoms;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+  // `sel` (optional): test only the columns sel[0 .. n_sel) of the [.][n] arrays; results go to out[sel[.]]
+  const int64_t count = sel ? n_sel : n;
+  for (int64_t w_i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w_i < count; w_i += warps) {
+    const int64_t i = sel ? __ldg(sel + w_i) : w_i;
     if (q) {
       // tree FK, level by level: lane j first builds its joint's local transform jointPlacement * Rot(axis, q_j), then
       // the joints of depth d (all independent) are composed with their parents' world placements of depth d - 1
@@ -130,22 +133,24 @@ template <> gik::DevScene<double>* scene_of<double>(gik_scene_dev* sd) { return 
 // list: 0 all pairs, 1 table/obstacle pairs, 2 cube's own pairs
 template <typename T>
 int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int list, double margin, int invert,
-                uint8_t* out, void* stream) {
+                uint8_t* out, void* stream, const int64_t* sel = nullptr, int64_t n_sel = 0) {
   if (bad_handle(h)) return GIK_E_HANDLE;
   if (n < 0) return GIK_E_SIZE;
   if (!(margin >= 0.0)) return GIK_E_PARAM;
   if (!h->scene) return GIK_E_NOSCENE;
-  if (n == 0) return GIK_OK;
+  if (n == 0 || (sel && n_sel == 0)) return GIK_OK;
+  if (n_sel < 0) return GIK_E_SIZE;
   if (!out || (list != 2 && !q) || (list == 2 && !cube_pose)) return GIK_E_NULL;
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   gik_scene_dev* sd = h->scene;
-  int64_t blocks = (n + gik::kCollideWarps - 1) / gik::kCollideWarps;
+  const int64_t work = sel ? n_sel : n;
+  int64_t blocks = (work + gik::kCollideWarps - 1) / gik::kCollideWarps;
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
   const uint8_t* pa = sd->pairs + (size_t)list * 2 * GIK_MAX_PAIRS;
   gik::gik_collision_kernel<T><<<(int)blocks, gik::kCollideWarps * 32, 0, (cudaStream_t)stream>>>(
-      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)margin, out, invert);
+      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)margin, out, invert, sel, n_sel);
   return (int)cudaGetLastError();
 }
 
@@ -198,6 +203,14 @@ int gik_scene_attach(gik_handle_t h, const gik_scene_t* scene) {
 
 int gik_collision_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 0, 0.0, 0, out, s); }
 int gik_collision_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 0, 0.0, 0, out, s); }
+int gik_collision_sel_f32(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const float* q, const float* cube, uint8_t* out, void* s) {
+  if (!sel) return GIK_E_NULL;
+  return collide_api<float>(h, n, q, cube, 0, 0.0, 0, out, s, sel, n_sel);
+}
+int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const double* q, const double* cube, uint8_t* out, void* s) {
+  if (!sel) return GIK_E_NULL;
+  return collide_api<double>(h, n, q, cube, 0, 0.0, 0, out, s, sel, n_sel);
+}
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double thr, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 1, thr, 1, out, s); }
 int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double thr, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 1, thr, 1, out, s); }
 int gik_cube_collision_f32(gik_handle_t h, int64_t n, const float* cube, uint8_t* out, void* s) { return collide_api<float>(h, n, (const float*)nullptr, cube, 2, 0.0, 0, out, s); }

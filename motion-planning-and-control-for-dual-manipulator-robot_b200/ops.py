@@ -249,15 +249,25 @@ class GraspIK:
                 raise RuntimeError("no collision scene attached: call GraspIK.attach_scene(scene) for this robot")
             self.attach_scene()
 
-    def collision_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None) -> torch.Tensor:
+    def collision_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None, sel: torch.Tensor | None = None) -> torch.Tensor:
         """tools.collision(robot, q) for every column: q [nq][n], cube_pose [12][n] (None = scene's cube placement)
-        -> colliding u8 [n]."""
+        -> colliding u8 [n].  `sel` (int64 [m], device): test only those columns (gik_collision_sel_*); the other
+        entries of the result are 0."""
         self._need_scene()
-        self._chk_dev(q_soa, cube_pose_soa)
+        self._chk_dev(q_soa, cube_pose_soa, sel)
         n = q_soa.shape[1]
+        cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
+        if sel is not None:
+            out = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+            f = getattr(self._lib, f"gik_collision_sel_{_sfx(q_soa.dtype)}")
+            sel = sel.to(torch.int64).contiguous()
+            _cabi.check(f(self._h, n, sel.numel(), self._ptr(sel), self._ptr(q_soa.contiguous()), self._ptr(cp), self._ptr(out),
+                          self._stream()), "gik_collision_sel")
+            if sel.numel():
+                self.launches += 1
+            return out
         out = torch.empty((n,), dtype=torch.uint8, device=self.device)
         f = getattr(self._lib, f"gik_collision_{_sfx(q_soa.dtype)}")
-        cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
         _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(cp), self._ptr(out), self._stream()), "gik_collision")
         if n:
             self.launches += 1
@@ -319,9 +329,7 @@ class GraspIK:
         # the predicate short-circuits (inverse_geometry.py:70): collision() is only evaluated where both residuals
         # pass, so only the converged columns are tested
         idx = torch.nonzero(convb).flatten()
-        col = torch.zeros_like(convb)
-        if idx.numel():
-            col[idx] = self.collision_soa(q[:, idx].contiguous(), pose[:, idx].contiguous()).bool()
+        col = self.collision_soa(q, pose, sel=idx).bool()
         success = convb & ~col
         pending = torch.nonzero(convb & col & (iters < max_iters)).flatten()
         if not descend_while_colliding:

@@ -216,3 +216,16 @@ def test_planner_trials_experiment(solver):
     r = res[0]
     assert r["std_dev"] == (0.1, 0.1, 0.1) and 0.0 <= r["success_rate"] <= 100.0
     assert r["success_rate"] >= 66.0 and r["min_iterations"] >= 1 and r["avg_time"] < 30.0
+
+
+def test_collision_on_a_column_subset(solver, table):
+    # gik_collision_sel_*: only the listed columns are tested (the predicate's short-circuit), the rest stay 0
+    Q, P = _inputs(table, 5000, 21)
+    qs, ps = _t(Q, torch.float32).t().contiguous(), _t(P, torch.float32).t().contiguous()
+    full = solver.collision_soa(qs, ps)
+    sel = torch.nonzero(torch.arange(5000, device="cuda:0") % 3 == 1).flatten()
+    part = solver.collision_soa(qs, ps, sel=sel)
+    assert torch.equal(part[sel], full[sel])
+    mask = torch.ones(5000, dtype=torch.bool, device="cuda:0"); mask[sel] = False
+    assert part[mask].sum().item() == 0
+    assert solver.collision_soa(qs, ps, sel=sel[:0]).sum().item() == 0
