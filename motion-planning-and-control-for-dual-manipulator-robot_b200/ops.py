@@ -259,12 +259,13 @@ class GraspIK:
         cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
         if sel is not None:
             out = torch.zeros((n,), dtype=torch.uint8, device=self.device)
+            if sel.numel() == 0:
+                return out
             f = getattr(self._lib, f"gik_collision_sel_{_sfx(q_soa.dtype)}")
             sel = sel.to(torch.int64).contiguous()
             _cabi.check(f(self._h, n, sel.numel(), self._ptr(sel), self._ptr(q_soa.contiguous()), self._ptr(cp), self._ptr(out),
                           self._stream()), "gik_collision_sel")
-            if sel.numel():
-                self.launches += 1
+            self.launches += 1
             return out
         out = torch.empty((n,), dtype=torch.uint8, device=self.device)
         f = getattr(self._lib, f"gik_collision_{_sfx(q_soa.dtype)}")
