@@ -225,6 +225,19 @@ int gik_collision_sel_f32(gik_handle_t h, int64_t n, int64_t n_sel, const int64_
 int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const double* q,
                           const double* cube_pose, uint8_t* colliding, void* stream);
 
+/* K3 + the collision term in ONE stream-ordered call without host synchronisation: the descent loop, then
+ * success[i] = converged[i] && !collision(q_out[:, i]) with collision() evaluated only on the converged problems
+ * (device-side compaction).  This is the reference's predicate (inverse_geometry.py:70, 97-98) evaluated ONCE at the
+ * configuration the descent stopped at; the reference additionally keeps descending while a converged iterate
+ * collides (re-testing after every update) -- GraspIK.solve_success_soa(descend_while_colliding=True) reproduces that
+ * tail with single-update re-entry rounds.  scratch: device, (n + 1) int64.  converged must not be NULL. */
+int gik_solve_success_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* params,
+                          float* q_out, uint8_t* success, uint8_t* converged, int32_t* iters, float* resid,
+                          int64_t* scratch, void* stream);
+int gik_solve_success_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* params,
+                          double* q_out, uint8_t* success, uint8_t* converged, int32_t* iters, double* resid,
+                          int64_t* scratch, void* stream);
+
 /* Replaces `distanceToObstacle(robot, q) >= threshold` (tools.py:38-51 with path.py:61-62): clear [n] = 1 when every
  * pair whose second geometry is the table or the obstacle is at least `threshold` apart. */
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, double threshold, uint8_t* clear, void* stream);

@@ -16,7 +16,8 @@ template <typename T>
 __global__ void __launch_bounds__(kCollideWarps * 32)
 gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pb,
                      int n_pairs, int64_t n, const T* __restrict__ q, const T* __restrict__ cube_pose, T margin,
-                     uint8_t* __restrict__ out, int invert, const int64_t* __restrict__ sel, int64_t n_sel) {
+                     uint8_t* __restrict__ out, int invert, const int64_t* __restrict__ sel, int64_t n_sel,
+                     const int64_t* __restrict__ n_sel_dev) {
   __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
   __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
   __shared__ uint16_t s_cand[kCollideWarps][kMaxCand];
@@ -24,7 +25,7 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
   const int nq = sc->tree.nq, ng = sc->n_geoms;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   // `sel` (optional): test only the columns sel[0 .. n_sel) of the [.][n] arrays; results go to out[sel[.]]
-  const int64_t count = sel ? n_sel : n;
+  const int64_t count = sel ? (n_sel_dev ? *n_sel_dev : n_sel) : n;
   for (int64_t w_i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w_i < count; w_i += warps) {
     const int64_t i = sel ? __ldg(sel + w_i) : w_i;
     if (q) {
@@ -106,6 +107,23 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
   }
 }
 
+// converged problems -> index list (order irrelevant) + count, everything else gets success = 0; one atomicAdd per warp
+__global__ void __launch_bounds__(256) gik_compact_converged_kernel(int64_t n, const uint8_t* __restrict__ conv,
+                                                                    uint8_t* __restrict__ success, int64_t* __restrict__ count,
+                                                                    int64_t* __restrict__ sel) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + lane;
+    const bool c = i < n && conv[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    long long base = 0;
+    if (lane == 0 && m) base = (long long)atomicAdd((unsigned long long*)count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (c) sel[base + __popc(m & ((1u << lane) - 1u))] = i;
+    else if (i < n) success[i] = 0;
+  }
+}
+
 }  // namespace gik
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -133,28 +151,51 @@ template <> gik::DevScene<double>* scene_of<double>(gik_scene_dev* sd) { return 
 // list: 0 all pairs, 1 table/obstacle pairs, 2 cube's own pairs
 template <typename T>
 int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int list, double margin, int invert,
-                uint8_t* out, void* stream, const int64_t* sel = nullptr, int64_t n_sel = 0) {
+                uint8_t* out, void* stream, const int64_t* sel = nullptr, int64_t n_sel = 0,
+                const int64_t* n_sel_dev = nullptr) {
   if (bad_handle(h)) return GIK_E_HANDLE;
   if (n < 0) return GIK_E_SIZE;
   if (!(margin >= 0.0)) return GIK_E_PARAM;
   if (!h->scene) return GIK_E_NOSCENE;
-  if (n == 0 || (sel && n_sel == 0)) return GIK_OK;
+  if (n == 0 || (sel && !n_sel_dev && n_sel == 0)) return GIK_OK;
   if (n_sel < 0) return GIK_E_SIZE;
   if (!out || (list != 2 && !q) || (list == 2 && !cube_pose)) return GIK_E_NULL;
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   gik_scene_dev* sd = h->scene;
-  const int64_t work = sel ? n_sel : n;
+  const int64_t work = (sel && !n_sel_dev) ? n_sel : n;     // device-side count: size the grid for the upper bound
   int64_t blocks = (work + gik::kCollideWarps - 1) / gik::kCollideWarps;
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
   const uint8_t* pa = sd->pairs + (size_t)list * 2 * GIK_MAX_PAIRS;
   gik::gik_collision_kernel<T><<<(int)blocks, gik::kCollideWarps * 32, 0, (cudaStream_t)stream>>>(
-      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)margin, out, invert, sel, n_sel);
+      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)margin, out, invert, sel, n_sel, n_sel_dev);
   return (int)cudaGetLastError();
 }
 
 }  // namespace
+
+// K3 + collision in one stream-ordered call, no host synchronisation: solve, compact the converged problems on the
+// device, test exactly those (the predicate's short-circuit) and write success = converged && !colliding.
+template <typename T>
+int solve_success_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, T* q_out,
+                      uint8_t* success, uint8_t* conv, int32_t* iters, T* resid, int64_t* scratch, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (!h->scene) return GIK_E_NOSCENE;
+  if (n > 0 && (!success || !conv || !scratch)) return GIK_E_NULL;
+  int rc = solve_api<T>(h, n, q_init, pose, prm, q_out, conv, iters, resid, stream);
+  if (rc || n == 0) return rc;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int64_t), st);
+  if (e != cudaSuccess) return (int)e;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+  gik::gik_compact_converged_kernel<<<(int)blocks, 256, 0, st>>>(n, conv, success, scratch, scratch + 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  return collide_api<T>(h, n, q_out, pose, 0, 0.0, 1, success, stream, scratch + 1, 0, scratch);
+}
 
 extern "C" {
 
@@ -210,6 +251,14 @@ int gik_collision_sel_f32(gik_handle_t h, int64_t n, int64_t n_sel, const int64_
 int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const double* q, const double* cube, uint8_t* out, void* s) {
   if (!sel) return GIK_E_NULL;
   return collide_api<double>(h, n, q, cube, 0, 0.0, 0, out, s, sel, n_sel);
+}
+int gik_solve_success_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p, float* q_out,
+                          uint8_t* success, uint8_t* conv, int32_t* iters, float* resid, int64_t* scratch, void* s) {
+  return solve_success_api<float>(h, n, q_init, pose, p, q_out, success, conv, iters, resid, scratch, s);
+}
+int gik_solve_success_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p, double* q_out,
+                          uint8_t* success, uint8_t* conv, int32_t* iters, double* resid, int64_t* scratch, void* s) {
+  return solve_success_api<double>(h, n, q_init, pose, p, q_out, success, conv, iters, resid, scratch, s);
 }
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double thr, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 1, thr, 1, out, s); }
 int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double thr, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 1, thr, 1, out, s); }

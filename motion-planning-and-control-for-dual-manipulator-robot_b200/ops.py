@@ -324,6 +324,24 @@ class GraspIK:
         would have freed the collision (and in the q returned for failed problems).
         -> (q [nq][n], success u8 [n], converged u8 [n], iters i32 [n], resid [2][n])."""
         self._need_scene()
+        if not descend_while_colliding:
+            # one stream-ordered C call, no host synchronisation: solve, device-side compaction, collision on the converged
+            self._chk_dev(q_init, pose)
+            n = q_init.shape[1]
+            q = torch.empty_like(q_init)
+            succ = torch.empty((n,), dtype=torch.uint8, device=self.device)
+            conv = torch.empty((n,), dtype=torch.uint8, device=self.device)
+            iters = torch.empty((n,), dtype=torch.int32, device=self.device)
+            resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
+            scratch = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+            prm = self._params(eps, dt, max_iters, damping, kernel, early_stop)
+            f = getattr(self._lib, f"gik_solve_success_{_sfx(q_init.dtype)}")
+            _cabi.check(f(self._h, n, self._ptr(q_init.contiguous()), self._ptr(pose.contiguous()), ctypes.byref(prm),
+                          self._ptr(q), self._ptr(succ), self._ptr(conv), self._ptr(iters), self._ptr(resid),
+                          self._ptr(scratch), self._stream()), "gik_solve_success")
+            if n:
+                self.launches += 3
+            return q, succ, conv, iters, resid
         q, conv, iters, resid = self.solve_soa(q_init, pose, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
                                                kernel=kernel, early_stop=early_stop)
         convb = conv.bool()
