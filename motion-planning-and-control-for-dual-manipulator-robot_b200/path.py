@@ -161,8 +161,8 @@ def project_path(robot, cube, q_curr, cube_curr, cube_rand, step_size=STEP_SIZE,
     # placements along the edge, same interpolation as the kernel, for the returned cube_path
     A = torch.from_numpy(a)[None].expand(n_ok, 12)
     B = torch.from_numpy(b)[None].expand(n_ok, 12)
-    alphas = [(k + 1) / num_steps for k in range(n_ok)]
-    poses = torch.cat([se3_interpolate(A[k:k + 1], B[k:k + 1], alphas[k]) for k in range(n_ok)], 0)
+    alphas = torch.arange(1, n_ok + 1, dtype=torch.float64) / num_steps
+    poses = se3_interpolate(A, B, alphas)
     bad = np.zeros(n_ok, bool)
     if cube_collision == "scene" or collision == "scene":
         pd = poses.to(solver.device, dtype).t().contiguous()

@@ -229,3 +229,23 @@ def test_collision_on_a_column_subset(solver, table):
     mask = torch.ones(5000, dtype=torch.bool, device="cuda:0"); mask[sel] = False
     assert part[mask].sum().item() == 0
     assert solver.collision_soa(qs, ps, sel=sel[:0]).sum().item() == 0
+
+
+def test_solve_success_call_edge_cases(solver):
+    # gik_solve_success_*: ragged sizes, nothing converged, empty batch
+    from conftest import make_poses
+    for n in (1, 33, 1000):
+        far = make_poses(n, 5); far[:, 9] += 3.0
+        q, succ, conv, it, res = solver.solve_success_soa(torch.zeros((15, n), device="cuda:0"),
+                                                          _t(far, torch.float32).t().contiguous(), descend_while_colliding=False)
+        assert succ.sum().item() == 0 and conv.sum().item() == 0 and (it == 1000).all()
+    P = make_poses(777, 6)
+    pose = _t(P, torch.float64).t().contiguous(); q0 = torch.zeros((15, 777), dtype=torch.float64, device="cuda:0")
+    q, succ, conv, it, res = solver.solve_success_soa(q0, pose, descend_while_colliding=False)
+    q2, conv2, it2, res2 = solver.solve_soa(q0, pose)
+    assert torch.equal(q, q2) and torch.equal(conv, conv2) and torch.equal(it, it2)
+    col = solver.collision_soa(q2, pose).bool()
+    assert torch.equal(succ.bool(), conv2.bool() & ~col)
+    q, succ, conv, it, res = solver.solve_success_soa(torch.zeros((15, 0), device="cuda:0"), torch.zeros((12, 0), device="cuda:0"),
+                                                      descend_while_colliding=False)
+    assert succ.numel() == 0
