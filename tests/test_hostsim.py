@@ -56,3 +56,31 @@ def test_hostsim_translation_sparsity_specialisation_is_exact(table_c, hostsim):
         a = hostsim.solve(table_c, np.zeros((16, 15)), P, dt, max_iters=50)
         b = hostsim.solve(table_c, np.zeros((16, 15)), P, dt, max_iters=50, flags=1)     # generic instantiation
         assert np.abs(a[0] - b[0]).max() < (1e-13 if dt == np.float64 else 1e-5)
+
+
+def test_hostsim_random_tables_of_the_supported_topology(table, hostsim, c_oracle):
+    # kernel math vs oracle on robots of the same topology but random dimensions / frames / limits (generic TZ = 0 path)
+    import copy
+    from conftest import rot_rpy
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        t = copy.deepcopy(table)
+        t.joint_p = t.joint_p * rng.uniform(0.85, 1.15, size=t.joint_p.shape) + rng.normal(scale=0.01, size=t.joint_p.shape)
+        t.hand_R = np.array([rot_rpy(*rng.uniform(-0.3, 0.3, 2), 1.5 + rng.normal(scale=0.3)) for _ in range(2)])
+        t.hand_p = t.hand_p + rng.normal(scale=0.01, size=(2, 3))
+        t.hook_R = np.array([rot_rpy(0, 0, rng.normal(scale=0.1)), rot_rpy(0, 0, -3.1 + rng.normal(scale=0.1))])
+        tc = t.to_c()
+        Q = rng.uniform(t.lower, t.upper, size=(32, 15))
+        R, p = c_oracle.fk(tc, Q)
+        J = c_oracle.jac(tc, Q)
+        R2, p2 = hostsim.fk(tc, Q, np.float64)
+        J2 = hostsim.jac(tc, Q, np.float64)
+        assert np.abs(R - R2).max() < 1e-12 and np.abs(p - p2).max() < 1e-12 and np.abs(J - J2).max() < 1e-12
+        P = make_poses(24, 100 + trial)
+        P[:, 9] = np.minimum(P[:, 9], 0.5)
+        qo, oko, ito, _ = c_oracle.solve(tc, np.zeros((24, 15)), P)
+        q, ok, it, r = hostsim.solve(tc, np.zeros((24, 15)), P, np.float64)
+        assert (ok == oko).all()
+        both = ok & oko
+        if both.any():
+            assert np.quantile(np.abs(q[both] - qo[both]).max(axis=1), 0.9) < 1e-9 and (it[both] == ito[both]).mean() > 0.9
