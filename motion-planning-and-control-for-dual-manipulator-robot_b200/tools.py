@@ -1,0 +1,99 @@
+"""The helpers of the reference's `tools.py` that sit on the IK path, with the same names and call shapes, backed by
+the flattened model / scene and the CUDA kernels instead of pinocchio + hpp-fcl:
+
+    jointlimitscost, jointlimitsviolated, projecttojointlimits   (tools.py:11-22)
+    collision(robot, q)                                          (tools.py:25-35)   -> gik_collision_*
+    distanceToObstacle(robot, q)                                 (tools.py:38-51)   -> gik_clearance_* (bisection)
+    getcubeplacement / setcubeplacement                          (tools.py:54-68)   -> the solver's current cube pose
+
+`robot` is whatever `solver_for` accepts (pinocchio RobotWrapper, KinematicTable, GraspIK, None = built-in Nextage).
+The cube placement that the reference stores inside the pinocchio geometry objects lives on the solver here
+(`solver.cube_pose`, a 12-vector); `setcubeplacement` updates it, `collision` / `distanceToObstacle` use it."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .inverse_geometry import _pose_to_array, _setcubeplacement, solver_for
+
+
+def _limits(robot):
+    s = solver_for(robot)
+    return np.asarray(s.table.lower, float), np.asarray(s.table.upper, float)
+
+
+def jointlimitscost(robot, q):
+    lo, hi = _limits(robot)
+    q = np.asarray(q, float)
+    return max(0.0, max(float(np.max(q - hi)), float(np.max(lo - q))))
+
+
+def jointlimitsviolated(robot, q):
+    """Return true if config not in joint limits (tools.py:17-19)."""
+    return jointlimitscost(robot, q) > 0.0
+
+
+def projecttojointlimits(robot, q):
+    lo, hi = _limits(robot)
+    return np.minimum(np.maximum(lo, np.asarray(q, float)), hi)
+
+
+def setcubeplacement(robot, cube, oMf):
+    """tools.setcubeplacement (tools.py:62-68): remember the cube placement for the following collision queries (and
+    write it into the pinocchio geometry objects when real pinocchio wrappers are passed)."""
+    s = solver_for(robot, cube)
+    s.cube_pose = _pose_to_array(oMf)
+    _setcubeplacement(robot, cube, oMf)
+
+
+def getcubeplacement(robot, hookname=None):
+    """tools.getcubeplacement (tools.py:54-59) as a 12-vector (rotation row-major, translation); with a hook name
+    ('LARM_HOOK' / 'RARM_HOOK') the placement of that hook frame, cube * hook offset."""
+    s = solver_for(robot)
+    pose = getattr(s, "cube_pose", None)
+    if pose is None:
+        s._need_scene()
+        g = s.scene.geoms[s.scene.cube]
+        pose = np.concatenate([np.asarray(g.R, float).reshape(9), np.asarray(g.p, float)])
+    if hookname is None:
+        return pose.copy()
+    h = {"LARM_HOOK": 0, "RARM_HOOK": 1}[hookname]
+    R, p = pose[:9].reshape(3, 3), pose[9:]
+    return np.concatenate([(R @ s.table.hook_R[h]).reshape(9), p + R @ s.table.hook_p[h]])
+
+
+def _q_soa(s, q, dtype):
+    return torch.as_tensor(np.asarray(q, float), dtype=dtype, device=s.device).reshape(1, -1).t().contiguous()
+
+
+def _cube_soa(s, dtype):
+    pose = getattr(s, "cube_pose", None)
+    return None if pose is None else torch.as_tensor(pose, dtype=dtype, device=s.device).reshape(1, 12).t().contiguous()
+
+
+def collision(robot, q, dtype=torch.float64):
+    """Return true if in collision, false otherwise (tools.py:25-35)."""
+    s = solver_for(robot)
+    return bool(s.collision_soa(_q_soa(s, q, dtype), _cube_soa(s, dtype))[0].item())
+
+
+def distanceToObstacle(robot, q, dtype=torch.float64, tol=1e-6, d_max=2.0):
+    """Shortest distance between the robot and the obstacle / table (tools.py:38-51).  The kernels answer
+    "every such pair is at least m apart" (gik_clearance_*); the distance is bracketed by evaluating a ladder of
+    margins in ONE batched call per refinement level.  Returns 0.0 when a pair intersects (hpp-fcl reports the negative
+    penetration depth there; every caller in the reference only compares the value with a positive threshold)."""
+    s = solver_for(robot)
+    s._need_scene()
+    qs, cs = _q_soa(s, q, dtype), _cube_soa(s, dtype)
+    lo, hi = 0.0, d_max
+    if not bool(s.clearance_soa(qs, cs, 0.0)[0].item()):
+        return 0.0
+    if bool(s.clearance_soa(qs, cs, hi)[0].item()):
+        return hi
+    while hi - lo > tol:                      # 16-way bracketing: ~5 rounds to 1e-6
+        ms = np.linspace(lo, hi, 18)[1:-1]
+        clear = [bool(s.clearance_soa(qs, cs, float(m))[0].item()) for m in ms]
+        k = sum(clear)                        # clearance is monotone in the margin
+        lo = ms[k - 1] if k > 0 else lo
+        hi = ms[k] if k < len(ms) else hi
+    return 0.5 * (lo + hi)

@@ -249,3 +249,23 @@ def test_solve_success_call_edge_cases(solver):
     q, succ, conv, it, res = solver.solve_success_soa(torch.zeros((15, 0), device="cuda:0"), torch.zeros((12, 0), device="cuda:0"),
                                                       descend_while_colliding=False)
     assert succ.numel() == 0
+
+
+def test_tools_module_dropins(solver, table, table_c, scene_c, c_oracle, golden):
+    # tools.py helpers with the reference's names (tools.py:11-68) on the GPU scene
+    from gik_b200 import tools
+    q0 = np.array(golden["cases"][0]["q"]); place = (np.eye(3), np.array(golden["cases"][0]["cube_p"]))
+    assert tools.collision(solver, np.zeros(15)) is True                       # lab_instructions.ipynb:252
+    tools.setcubeplacement(solver, None, place)
+    assert np.abs(tools.getcubeplacement(solver)[9:] - place[1]).max() == 0
+    assert np.abs(tools.getcubeplacement(solver, "LARM_HOOK")[9:] - (place[1] + [0, 0.05, 0])).max() < 1e-15
+    assert tools.collision(solver, q0) is False
+    P = np.concatenate([np.eye(3).reshape(9), place[1]])[None]
+    d_ref = c_oracle.scene_distance(table_c, scene_c, q0[None], P, mode=1)[0]
+    d = tools.distanceToObstacle(solver, q0)
+    assert abs(d - d_ref) < 1e-5 and d > 0
+    assert tools.distanceToObstacle(solver, np.zeros(15)) == 0.0               # hands inside the table at q0
+    q_bad = q0.copy(); q_bad[3] = 2.0
+    assert tools.jointlimitsviolated(solver, q_bad) and not tools.jointlimitsviolated(solver, q0)
+    assert abs(tools.jointlimitscost(solver, q_bad) - (2.0 - table.upper[3])) < 1e-12
+    assert np.array_equal(tools.projecttojointlimits(solver, q_bad), np.minimum(np.maximum(table.lower, q_bad), table.upper))
