@@ -18,8 +18,19 @@ from .inverse_geometry import _pose_to_array, _setcubeplacement, solver_for
 
 
 def _limits(robot):
-    s = solver_for(robot)
-    return np.asarray(s.table.lower, float), np.asarray(s.table.upper, float)
+    """Joint limits without touching the GPU: from the table, the pinocchio model or the built-in Nextage constants."""
+    from .model import KinematicTable, nextage_table
+    from .ops import GraspIK
+    if isinstance(robot, GraspIK):
+        t = robot.table
+    elif isinstance(robot, KinematicTable):
+        t = robot
+    elif robot is None:
+        t = nextage_table()
+    else:
+        m = getattr(robot, "model", robot)
+        return np.asarray(m.lowerPositionLimit, float).reshape(-1), np.asarray(m.upperPositionLimit, float).reshape(-1)
+    return np.asarray(t.lower, float), np.asarray(t.upper, float)
 
 
 def jointlimitscost(robot, q):

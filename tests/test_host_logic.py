@@ -55,3 +55,13 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_joint_limit_helpers_need_no_gpu(table):
+    # tools.py:11-22 with the reference's names; limits come from the table / model, not from a device handle
+    from gik_b200 import tools
+    q = np.zeros(15); q[4] = 5.0; q[7] = -9.0
+    p = tools.projecttojointlimits(None, q)
+    assert p[4] == table.upper[4] and p[7] == table.lower[7] and np.array_equal(p[[0, 1, 2]], [0, 0, 0])
+    assert tools.jointlimitsviolated(table, q) and not tools.jointlimitsviolated(table, p)
+    assert abs(tools.jointlimitscost(table, q) - max(5.0 - table.upper[4], table.lower[7] + 9.0)) < 1e-12
