@@ -172,8 +172,10 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
     1..R-1 from configurations drawn uniformly inside the joint limits; the best converged candidate (smallest
     max residual, ties -> lowest restart) is returned (BASELINE config 3).  `collision=True` makes the returned flag
     the reference's full `success` (converged and collision-free on the attached scene, with the reference's
-    keep-descending-while-colliding behaviour: GraspIK.solve_success_soa); the default returns `converged` only (the
-    north_star's kernel contract; `apply_collision` applies a host-side test afterwards)."""
+    keep-descending-while-colliding behaviour: GraspIK.solve_success_soa); `collision="once"` evaluates the collision
+    term once at the configuration the descent stopped at (one sync-free call, gik_solve_success_*: same decisions
+    unless further descent would have freed a collision); the default returns `converged` only (the north_star's
+    kernel contract; `apply_collision` applies a host-side test afterwards)."""
     solver = solver_for(robot, cube)
     host_in = (not torch.is_tensor(cube_pose) or not cube_pose.is_cuda) and (not torch.is_tensor(q_init) or not q_init.is_cuda)
     if host_in and not collision and restarts <= 1 and torch.is_tensor(cube_pose):
@@ -187,7 +189,8 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
         if qi.dim() == 1:
             qi = qi.unsqueeze(0).expand(B, solver.nq)
         q, succ, conv, iters, resid = solver.solve_success_soa(qi.t().contiguous(), p12.t().contiguous(), eps=eps, dt=dt,
-                                                              max_iters=max_iters, damping=damping)
+                                                              max_iters=max_iters, damping=damping,
+                                                              descend_while_colliding=(collision != "once"))
         res = (q.t(), succ.bool())
         if return_info:
             from .ops import SolveInfo
