@@ -94,18 +94,24 @@ GIK_HD float rsqrt_(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
-// fp64 device versions: MUFU seed (rsqrt/rcp.approx.ftz.f64, ~1e-6 relative) + two Newton steps.  Measured on B200
-// over 1e-12..1e12 (tools/probes/f64_approx.cu): max relative error 1.9e-16 (rsqrt), 1.1e-16 (rcp) -- as good as the
-// library forms at 7 / 5 FP64-pipe instructions instead of 12 / 22 (no special-case paths: operands are floored).
+// fp64 device versions: MUFU seed (rsqrt/rcp.approx.ftz.f64, ~2^-22 relative) + ONE third-order correction step
+// (5 / 3 FP64-pipe instructions; two Newton steps, 7 / 4, behind GIK_NEWTON2_F64).  Accuracy measured on B200 over
+// 1e-12..1e12 by tools/probes/f64_approx.cu; no special-case paths: operands are floored.
 GIK_HD double rsqrt_(double x) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#ifdef GIK_NEWTON2_F64
   const double h = 0.5 * x;
   double e = fma(-h * y, y, 0.5);
   y = fma(y, e, y);
   e = fma(-h * y, y, 0.5);
   return fma(y, e, y);
+#else
+  // one third-order step: y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2; seed error 2^-22 -> ~1e-20 before rounding
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(e, 0.375, 0.5), y);
+#endif
 #else
   return 1.0 / sqrt(x);
 #endif
@@ -123,10 +129,16 @@ GIK_HD double div_(double a, double b) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+#ifdef GIK_NEWTON2_F64
   double e = fma(-b, y, 1.0);
   y = fma(y, e, y);
   e = fma(-b, y, 1.0);
   return a * fma(y, e, y);
+#else
+  // one third-order step: y (1 + e + e^2), e = 1 - b y
+  const double e = fma(-b, y, 1.0);
+  return a * fma(fma(y, e, y), e, y);
+#endif
 #else
   return a / b;
 #endif
@@ -164,7 +176,41 @@ GIK_HD float atan2_pos(float y, float x) {
   r = y > ax ? 1.57079632679489662f - r : r;
   return x < 0.0f ? 3.14159265358979324f - r : r;
 }
-GIK_HD double atan2_pos(double y, double x) { return atan2(y, x); }
+// fp64: one division + a degree-10 polynomial in u^2 after reducing the ratio to |u| <= tan(pi/8)
+// (mn/mx > tan(pi/8): atan(mn/mx) = pi/4 + atan((mn - mx)/(mn + mx))).  Coefficients: interpolation of
+// (atan(u) - u)/u^3 at the Chebyshev nodes of u^2 in [0, tan^2(pi/8)], computed in 50-digit arithmetic; max abs error
+// of the double evaluation 5.6e-17 on a 2001-point grid (= rounding).  Branch-free, constants are constant-bank
+// loads on the device (the library atan2 spends ~40 UMOV on its 64-bit immediates plus a division slow path).
+#define GIK_ATAN64_COEFFS                                                                                      \
+  -0.3333333333333333, 0.1999999999999552, -0.14285714284666542, 0.11111111015256361, -0.09090904578123903,  \
+      0.07692183190826087, -0.06664511447381948, 0.0585814891280221, -0.0508544973794026, 0.03923165829558719, \
+      -0.01917688711906226
+#if defined(__CUDACC__) && !defined(GIK_LIB_ATAN64)
+static __constant__ double kAtan64[11] = {GIK_ATAN64_COEFFS};
+#endif
+GIK_HD double atan2_pos(double y, double x) {
+#if defined(GIK_LIB_ATAN64)
+  return atan2(y, x);
+#else
+#ifdef __CUDA_ARCH__
+  const double* K = kAtan64;
+#else
+  static const double K[11] = {GIK_ATAN64_COEFFS};
+#endif
+  const double ax = fabs(x);
+  const double mn = min_(y, ax), mx = max_(max_(y, ax), 1e-300);
+  const bool big = mn > 0.41421356237309503 * mx;
+  const double num = big ? mn - mx : mn, den = big ? mn + mx : mx;
+  const double u = div_(num, den), z = u * u;
+  double p = fma(K[10], z, K[9]);
+  p = fma(p, z, K[8]); p = fma(p, z, K[7]); p = fma(p, z, K[6]); p = fma(p, z, K[5]);
+  p = fma(p, z, K[4]); p = fma(p, z, K[3]); p = fma(p, z, K[2]); p = fma(p, z, K[1]); p = fma(p, z, K[0]);
+  double r = fma(u * z, p, u);
+  r = big ? r + 0.78539816339744831 : r;
+  r = y > ax ? 1.57079632679489662 - r : r;
+  return x < 0.0 ? 3.14159265358979324 - r : r;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------------
 // F2: two fp32 values in one 64-bit register pair, operated on by Blackwell's packed FFMA2 / FMUL2 / FADD2
@@ -231,9 +277,61 @@ GIK_HD void sincos_(float x, float& s, float& c) {
   s = sinf(x); c = cosf(x);
 #endif
 }
+// fp64, FAST: Cody-Waite reduction by multiples of pi/2 (two-term pi/2, exact-product FMAs) + the classic degree-13 /
+// degree-14 minimax kernels on |r| <= pi/4 (coefficients of the fdlibm __kernel_sin / __kernel_cos polynomials;
+// < 1 ulp each).  Same arithmetic class as the library sincos, but every constant is a constant-bank OPERAND of its
+// DFMA: the library form materialises its 64-bit immediates with UMOV pairs inside the descent loop (~30 per call,
+// 15 % of the loop's issue slots in the round-1 fp64 capture) and carries a slow-path branch for huge arguments.
+// Valid for |x| < 2^50 (far beyond any joint range); NaN/inf propagate.
+#if defined(__CUDACC__)
+#ifndef GIK_LIB_SINCOS64
+static __constant__ double kSinCos64[18] = {
+    6.36619772367581382433e-01,   // 0: 2/pi
+    6755399441055744.0,           // 1: 1.5 * 2^52 (round-to-nearest-integer magic)
+    -1.57079632679489655800e+00,  // 2: -(pi/2 high)
+    -6.12323399573676603587e-17,  // 3: -(pi/2 low)
+    -1.66666666666666324348e-01,  // 4: S1
+    8.33333333332248946124e-03,   // 5: S2
+    -1.98412698298579493134e-04,  // 6: S3
+    2.75573137070700676789e-06,   // 7: S4
+    -2.50507602534068634195e-08,  // 8: S5
+    1.58969099521155010221e-10,   // 9: S6
+    4.16666666666666019037e-02,   // 10: C1
+    -1.38888888888741095749e-03,  // 11: C2
+    2.48015872894767294178e-05,   // 12: C3
+    -2.75573143513906633035e-07,  // 13: C4
+    2.08757232129817482790e-09,   // 14: C5
+    -1.13596475577881948265e-11,  // 15: C6
+    -0.5, 1.0};
+#endif
+#endif
 template <bool FAST>
 GIK_HD void sincos_(double x, double& s, double& c) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(GIK_LIB_SINCOS64)
+  if (FAST) {
+    const double* K = kSinCos64;
+    const double t = fma(x, K[0], K[1]);
+    const int k = __double2loint(t);
+    const double kd = t - K[1];
+    double r = fma(kd, K[2], x);
+    r = fma(kd, K[3], r);
+    const double z = r * r;
+    double ps = fma(K[9], z, K[8]);
+    ps = fma(ps, z, K[7]); ps = fma(ps, z, K[6]); ps = fma(ps, z, K[5]); ps = fma(ps, z, K[4]);
+    double pc = fma(K[15], z, K[14]);
+    pc = fma(pc, z, K[13]); pc = fma(pc, z, K[12]); pc = fma(pc, z, K[11]); pc = fma(pc, z, K[10]);
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(z, K[16], K[17]));
+    const bool odd = k & 1;
+    double so = odd ? cr : sr, co = odd ? sr : cr;
+    // sign flips on the high word: sin negative in quadrants 2, 3; cos negative in quadrants 1, 2
+    so = __hiloint2double(__double2hiint(so) ^ ((k & 2) << 30), __double2loint(so));
+    co = __hiloint2double(__double2hiint(co) ^ (((k + 1) & 2) << 30), __double2loint(co));
+    s = so; c = co;
+  } else {
+    sincos(x, &s, &c);
+  }
+#elif defined(__CUDA_ARCH__)
   sincos(x, &s, &c);
 #else
   s = sin(x); c = cos(x);

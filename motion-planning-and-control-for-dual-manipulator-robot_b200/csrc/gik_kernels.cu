@@ -407,7 +407,9 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 #define GIK_MINB_PAIR_F32 5
 #endif
 #ifndef GIK_MINB_PAIR_F64
-#define GIK_MINB_PAIR_F64 4   // 128 registers + L1 spills: measured best (7.07M vs 6.91M at 3, 6.26M at 2 blocks/SM)
+#define GIK_MINB_PAIR_F64 3   // 168 registers, 12 warps / SM.  With the constant-bank sincos / atan2 the loop is bound by its FP64-pipe
+                              // instruction count, not by latency: 8, 9, 10, 11, 12 warps / SM all measure 9.2-9.5 M solves/s
+                              // (2^20 problems), 14 and 16 warps (144 / 128 registers + spills) 9.1 / 8.9 M
 #endif
 template <typename T> struct LaunchPair;
 template <> struct LaunchPair<float>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
