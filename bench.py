@@ -474,7 +474,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (gik_solve_kernel): CUDA-core FMA pipe, peak measured in this run
+    # ---- roofline of the dominant kernel (the solve kernel the launcher picked): CUDA-core FMA pipe, peak measured in this run
     fpi = gik_b200.flops_per_iter()
     peak = gik_b200.fma_peak_tflops(local, esz)
     iters_per_launch = iters_sum / world
@@ -491,7 +491,9 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {
-        "bound": "fp32" if esz == 4 else "fp64", "kernel": "gik_solve_kernel",
+        "bound": "fp32" if esz == 4 else "fp64",
+        "kernel": solver.kernel_name(wl.E if args.config == 4 else wl.solves, dtype, args.kernel)
+        + (" (edge mode)" if args.config == 4 else ""),
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
         "peak_source": "measured in this run: register-resident FMA chains on every SM (gik_measure_fma_peak); "
                        "MEASURED_PEAKS.json has no CUDA-core figure",

@@ -258,6 +258,9 @@ size_t gik_bytes_per_solve(int elem_size);
 int gik_measure_fma_peak(int device, int elem_size, int repeats, double* tflops);
 /* Grid the solver launches for n problems on the handle's device (for gpu_launches / occupancy reports). */
 int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blocks, int32_t* threads);
+/* Name of the kernel gik_solve_* launches for n problems with params.flags = flags (static string; "" on bad
+ * arguments).  For reports: bench.py's roofline.kernel. */
+const char* gik_solve_kernel_name(gik_handle_t h, int elem_size, int64_t n, int flags);
 
 const char* gik_strerror(int code);
 const char* gik_version(void);

@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
     L.gik_bytes_per_solve.argtypes = [ctypes.c_int]; L.gik_bytes_per_solve.restype = ctypes.c_size_t
     L.gik_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.gik_solve_launch_dims.argtypes = [_P, ctypes.c_int, _I64, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]
+    L.gik_solve_kernel_name.argtypes = [_P, ctypes.c_int, _I64, ctypes.c_int]
+    L.gik_solve_kernel_name.restype = ctypes.c_char_p
     L.gik_strerror.argtypes = [ctypes.c_int]; L.gik_strerror.restype = ctypes.c_char_p
     L.gik_version.restype = ctypes.c_char_p
     _lib = L
@@ -114,6 +116,7 @@ EXPORTS = [
     "gik_scene_attach", "gik_collision_f32", "gik_collision_f64", "gik_collision_sel_f32", "gik_collision_sel_f64", "gik_solve_success_f32", "gik_solve_success_f64", "gik_clearance_f32", "gik_clearance_f64",
     "gik_cube_collision_f32", "gik_cube_collision_f64",
     "gik_flops_per_iter", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",
+    "gik_solve_kernel_name",
     "gik_strerror", "gik_version",
 ]
 

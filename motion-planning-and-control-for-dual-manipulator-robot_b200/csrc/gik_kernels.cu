@@ -1069,6 +1069,20 @@ int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blo
   return GIK_OK;
 }
 
+const char* gik_solve_kernel_name(gik_handle_t h, int elem_size, int64_t n, int flags) {
+  if (bad_handle(h) || n < 0 || (elem_size != 4 && elem_size != 8)) return "";
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return "";
+  int b = 0, l = 32, rc;
+  bool pair = false;
+  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, flags, &b, &l, &pair);
+  else rc = choose_launch<double, MODE_BATCH>(h, n, flags, &b, &l, &pair);
+  if (rc) return "";
+  if (pair) return elem_size == 4 ? "gik_solve_pair_kernel<float>" : "gik_solve_pair_kernel<double>";
+  if (elem_size == 8) return "gik_solve_kernel<double>";
+  return (flags & GIK_F_SCALAR_LANE) ? "gik_solve_kernel<float>" : "gik_solve_lane2_kernel";
+}
+
 const char* gik_strerror(int code) {
   switch (code) {
     case GIK_OK: return "ok";

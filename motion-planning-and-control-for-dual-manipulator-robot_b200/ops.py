@@ -103,6 +103,11 @@ class GraspIK:
         flags = self._KERNEL_FLAGS[kernel] | (16 if early_stop else 0)        # GIK_F_EARLY_STOP
         return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), flags)
 
+    def kernel_name(self, n, dtype=torch.float32, kernel=None) -> str:
+        """Kernel the batch solve launches for n problems (gik_solve_kernel_name); for reports."""
+        esz = 4 if dtype == torch.float32 else 8
+        return self._lib.gik_solve_kernel_name(self._h, esz, int(n), self._KERNEL_FLAGS[kernel]).decode()
+
     def _chk_dev(self, *ts):
         for t in ts:
             if t is not None and (not t.is_cuda or t.device != self.device):
