@@ -46,6 +46,7 @@ struct ArmConst {
   T finv_R[9];  // (hand frame offset on the tip joint)^-1, row-major
   T finv_p[3];
   T tip_lin[3]; // finv_p x finv_R[:, axis of the tip joint]: linear part of the (constant) LOCAL Jacobian column of the tip joint
+  T g6[21];     // lower triangle (i >= j at i(i+1)/2 + j) of tip_col tip_col^T: the tip joint's constant share of G = A A^T
   T hook_R[9];  // hook frame on the cube
   T hook_p[3];
 };
@@ -489,7 +490,7 @@ struct HandState {
   T yf[6], zf[6];
 };
 
-template <typename T, int OFF, uint32_t TZ>
+template <typename T, int OFF, uint32_t TZ, bool G6 = true>
 GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
                         T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
   T B[9], b[3], A[6][7], e[6];
@@ -497,15 +498,35 @@ GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (
   hand_error(B, b, tgt, e);
   resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
 
-  // Cholesky of G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle, in place
+  // G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle.  Two structural facts of the compiled chain save 30 of the
+  // 126 products: the tip joint's column is constant, so its outer product comes from the table (ac.g6; G6 = false
+  // keeps the products -- the pair kernels read their arm constants by lane-dependent constant loads, where 21 more
+  // loads cost a latency-bound chain more than 21 multiplies: config 4 measured 45.1 ms with the table against 40.3); and chain
+  // joints 2 and 3 turn about the same axis with a rotation-free placement between them, so their angular parts
+  // A[3..5][2] and A[3..5][3] are the same values -- the angular-angular block takes 2 a a^T once and the
+  // angular-linear block takes a (l_2 + l_3)^T.
+  static_assert(chain_axis(2) == chain_axis(3), "parallel consecutive axes assumed by the Gram shortcut");
   T (&L)[6][6] = hs.L;
+  T l23[3], a2[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { l23[j] = A[j][2] + A[j][3]; a2[j] = A[3 + j][2] + A[3 + j][2]; }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j <= i; ++j) {
-      T g = (i == j) ? A[i][1] * A[j][1] + lambda : A[i][1] * A[j][1];
-#pragma unroll
-      for (int k = 2; k <= 6; ++k) g += A[i][k] * A[j][k];
+      T g;
+      if constexpr (G6) {
+        const T g0 = (i == j) ? ac.g6[i * (i + 1) / 2 + j] + lambda : ac.g6[i * (i + 1) / 2 + j];
+        g = A[i][1] * A[j][1] + g0;
+      } else {
+        g = (i == j) ? A[i][1] * A[j][1] + lambda : A[i][1] * A[j][1];
+        g += A[i][6] * A[j][6];
+      }
+      if (i >= 3 && j >= 3) g += a2[i - 3] * A[j][2];
+      else if (i >= 3) g += A[i][2] * l23[j];
+      else { g += A[i][2] * A[j][2]; g += A[i][3] * A[j][3]; }
+      g += A[i][4] * A[j][4];
+      g += A[i][5] * A[j][5];
       L[i][j] = g;
     }
 #pragma unroll
@@ -574,8 +595,10 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
   HandState<T> hL, hR;
   T SyL, SzL, SyR, SzR;
-  hand_phase1<T, 0, TZ>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
-  hand_phase1<T, 6, TZ>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
+  // the fp64 lane kernel keeps the tip products so that it stays bit-identical to the fp64 pair kernel (the default)
+  constexpr bool G6 = sizeof(T) == 4;
+  hand_phase1<T, 0, TZ, G6>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
+  hand_phase1<T, 6, TZ, G6>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
   const T kappa = chest_rate(SyL, SzL, SyR, SzR);
   dq[0] = kappa;
   T dL[6], dR[6];

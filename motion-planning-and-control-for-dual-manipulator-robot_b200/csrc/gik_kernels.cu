@@ -484,7 +484,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     HandState<T> hs;
 #pragma unroll
     for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
-    hand_phase1<T, 0, TZ>(ac, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
+    hand_phase1<T, 0, TZ, false>(ac, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
     const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
     const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
     const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);

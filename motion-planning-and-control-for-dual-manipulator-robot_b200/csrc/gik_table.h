@@ -100,6 +100,11 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
       ac.tip_lin[0] = (T)(fi_p[1] * av[2] - fi_p[2] * av[1]);
       ac.tip_lin[1] = (T)(fi_p[2] * av[0] - fi_p[0] * av[2]);
       ac.tip_lin[2] = (T)(fi_p[0] * av[1] - fi_p[1] * av[0]);
+      // the tip column as the kernels see it (rounded to T), and its outer product
+      const double col[6] = {(double)ac.tip_lin[0], (double)ac.tip_lin[1], (double)ac.tip_lin[2],
+                             (double)(T)av[0], (double)(T)av[1], (double)(T)av[2]};
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) ac.g6[i * (i + 1) / 2 + j] = (T)(col[i] * col[j]);
     }
     for (int i = 0; i < 9; ++i) ac.hook_R[i] = (T)t.hook_R[h][i];
     for (int i = 0; i < 3; ++i) ac.hook_p[i] = (T)t.hook_p[h][i];
@@ -122,6 +127,7 @@ inline void build_packed_table(const DevTable<float>& d, PackedTable& p) {
   for (int k = 0; k < 7; ++k)
     for (int i = 0; i < 3; ++i) p.arm.t[k][i] = F2(L.t[k][i], R.t[k][i]);
   for (int i = 0; i < 9; ++i) { p.arm.finv_R[i] = F2(L.finv_R[i], R.finv_R[i]); p.arm.hook_R[i] = F2(L.hook_R[i], R.hook_R[i]); }
+  for (int i = 0; i < 21; ++i) p.arm.g6[i] = F2(L.g6[i], R.g6[i]);
   for (int i = 0; i < 3; ++i) {
     p.arm.finv_p[i] = F2(L.finv_p[i], R.finv_p[i]);
     p.arm.tip_lin[i] = F2(L.tip_lin[i], R.tip_lin[i]);
