@@ -404,7 +404,9 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 // Arm constants are lane dependent: they come from the kernel-parameter table by indexed constant loads.
 // ========================================================================================================
 #ifndef GIK_MINB_PAIR_F32
-#define GIK_MINB_PAIR_F32 5
+#define GIK_MINB_PAIR_F32 3   // 165 registers: the hand's constants live in registers (HOIST below).  Measured against the
+                              // 96-register build with lane-indexed constant loads: config 4 40.1 -> 32.0 ms, 16 Ki problems
+                              // 1.33 -> 1.02 ms, 2 Ki problems 0.89 -> 0.67 ms (the same code capped at 96 registers: 44.5 ms)
 #endif
 #ifndef GIK_MINB_PAIR_F64
 #define GIK_MINB_PAIR_F64 3   // 168 registers, 12 warps / SM.  With the constant-bank sincos / atan2 the loop is bound by its FP64-pipe
@@ -424,7 +426,32 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
   const int64_t n = a.n;
   const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
-  const ArmConst<T>& ac = tab.arm[h];
+  // fp32: this kernel serves batches too small to fill the machine (edge chains, single solves), where the time is the
+  // LATENCY of one chain and registers are free -- so the hand's constants are selected into registers once instead
+  // of being fetched by lane-indexed constant loads (39 LDC + their scoreboard waits per iteration), and the tip
+  // joint's constant outer product can then come from the table as in the lane kernels.  fp64 (also the large-batch
+  // kernel, bound by the FP64 pipe at 168 registers) keeps the constant loads.
+  constexpr bool HOIST = sizeof(T) == 4;
+  ArmConst<T> acr;
+  T lim_lo[7], lim_hi[7];
+  if constexpr (HOIST) {
+    const ArmConst<T>&L = tab.arm[0], &R = tab.arm[1];
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) acr.t[k][i] = h ? R.t[k][i] : L.t[k][i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acr.finv_R[i] = h ? R.finv_R[i] : L.finv_R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { acr.finv_p[i] = h ? R.finv_p[i] : L.finv_p[i]; acr.tip_lin[i] = h ? R.tip_lin[i] : L.tip_lin[i]; }
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acr.g6[i] = h ? R.g6[i] : L.g6[i];
+    lim_lo[0] = tab.lo[0]; lim_hi[0] = tab.hi[0];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { lim_lo[1 + k] = h ? tab.lo[7 + k] : tab.lo[1 + k]; lim_hi[1 + k] = h ? tab.hi[7 + k] : tab.hi[1 + k]; }
+  }
+  const ArmConst<T>& ac = tab.arm[h];           // rare paths (hook targets at a refill / edge step) and fp64
+  const ArmConst<T>& acl = HOIST ? acr : tab.arm[h];   // descent loop
 
   T q[7], tgt[12];                              // q[0] = chest (kept by both lanes), q[1..6] = this hand's arm
 #pragma unroll
@@ -484,7 +511,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     HandState<T> hs;
 #pragma unroll
     for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
-    hand_phase1<T, 0, TZ, false>(ac, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
+    hand_phase1<T, 0, TZ, HOIST>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
     const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
     const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
     const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
@@ -500,10 +527,16 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     const bool done = ok || (it >= a.max_iters) || stalled;
 
     if (!done) {
-      q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
+      if constexpr (HOIST) {
+        q[0] = min_(max_(lim_lo[0], q[0] + a.dt * kappa), lim_hi[0]);
 #pragma unroll
-      for (int k = 0; k < 6; ++k)
-        q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * dqa[k]), tab.hi[off + k]);
+        for (int k = 0; k < 6; ++k) q[1 + k] = min_(max_(lim_lo[1 + k], q[1 + k] + a.dt * dqa[k]), lim_hi[1 + k]);
+      } else {
+        q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * dqa[k]), tab.hi[off + k]);
+      }
       ++it;
     } else if (active) {
       const bool batch = (MODE == MODE_BATCH);
