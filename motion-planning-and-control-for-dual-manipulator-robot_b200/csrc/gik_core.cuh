@@ -30,6 +30,16 @@
 #define GIK_MAX_NQ 32
 #endif
 
+#ifndef GIK_LATE_LANE
+#define GIK_LATE_LANE false
+#endif
+#ifndef GIK_LATE_LANE2
+#define GIK_LATE_LANE2 false
+#endif
+#ifndef GIK_LATE_PAIR
+#define GIK_LATE_PAIR false
+#endif
+
 namespace gik {
 
 constexpr int kActive = 13;  // chest + 6 + 6 joints that move the hands
@@ -344,26 +354,21 @@ GIK_HD void sincos_(double x, double& s, double& c) {
 // inverse_geometry.py:66-67); theta is taken as atan2(|vee(R - R^T)|/2, (tr R - 1)/2), which equals
 // acos((tr R - 1)/2) for a rotation matrix but stays accurate in fp32 near theta = 0.
 // ------------------------------------------------------------------------------------------------------
+// The function is split in two so that a caller can put independent work between the halves: log6_pre is straight-line
+// code (theta, the common-case w = theta/(2 sin theta) vee(R - R^T), alpha, beta -- a chain of dependent MUFU results),
+// log6_post holds the one data-dependent branch (pinocchio's form near theta = pi, rare) and the assembly of [v; w].
 template <typename T>
-GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
+struct Log6Mid { T vx, vy, vz, d0, d1, d2, c, theta, wx, wy, wz, alpha, beta; };
+
+template <typename T>
+GIK_HD void log6_pre(const T (&R)[9], Log6Mid<T>& m) {
   const T vx = R[7] - R[5], vy = R[2] - R[6], vz = R[3] - R[1];
   const T tr = R[0] + R[4] + R[8];
   const T c = min_(max_((tr - T(1)) * T(0.5), T(-1)), T(1));
   const T s = T(0.5) * sqrt_(vx * vx + vy * vy + vz * vz);
   const T theta = atan2_pos(s, c);
-  T wx, wy, wz;
-  if (theta >= T(3.14159265358979323846 - 1e-2)) {
-    // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
-    const T cphi = -c;
-    const T beta = div_(theta * theta, T(1) + cphi);
-    const T t0 = (R[0] + cphi) * beta, t1 = (R[4] + cphi) * beta, t2 = (R[8] + cphi) * beta;
-    wx = (vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
-    wy = (vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
-    wz = (vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
-  } else {
-    const T fac = s > Num<T>::kTinyS ? T(0.5) * div_(theta, s) : T(0.5);  // theta / (2 sin theta)
-    wx = fac * vx; wy = fac * vy; wz = fac * vz;
-  }
+  const T fac = s > Num<T>::kTinyS ? T(0.5) * div_(theta, s) : T(0.5);  // theta / (2 sin theta)
+  m.wx = fac * vx; m.wy = fac * vy; m.wz = fac * vz;
   const T t2 = theta * theta;
   // alpha = (theta/2) cot(theta/2), beta = (1 - alpha) / theta^2; cot(theta/2) = (1+c)/s = s/(1-c)
   const bool front = c >= T(0);
@@ -375,11 +380,34 @@ GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
     alpha = T(1) - t2 * (T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * T(1.0 / 30240)));
     beta = T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * (T(1.0 / 30240) + t2 * T(1.0 / 1209600)));
   }
-  const T wp = beta * (wx * p[0] + wy * p[1] + wz * p[2]);
-  e[0] = alpha * p[0] - T(0.5) * (wy * p[2] - wz * p[1]) + wp * wx;
-  e[1] = alpha * p[1] - T(0.5) * (wz * p[0] - wx * p[2]) + wp * wy;
-  e[2] = alpha * p[2] - T(0.5) * (wx * p[1] - wy * p[0]) + wp * wz;
+  m.vx = vx; m.vy = vy; m.vz = vz; m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
+  m.c = c; m.theta = theta; m.alpha = alpha; m.beta = beta;
+}
+
+template <typename T>
+GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
+  T wx = m.wx, wy = m.wy, wz = m.wz;
+  if (m.theta >= T(3.14159265358979323846 - 1e-2)) {
+    // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
+    const T cphi = -m.c;
+    const T beta = div_(m.theta * m.theta, T(1) + cphi);
+    const T t0 = (m.d0 + cphi) * beta, t1 = (m.d1 + cphi) * beta, t2 = (m.d2 + cphi) * beta;
+    wx = (m.vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
+    wy = (m.vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
+    wz = (m.vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
+  }
+  const T wp = m.beta * (wx * p[0] + wy * p[1] + wz * p[2]);
+  e[0] = m.alpha * p[0] - T(0.5) * (wy * p[2] - wz * p[1]) + wp * wx;
+  e[1] = m.alpha * p[1] - T(0.5) * (wz * p[0] - wx * p[2]) + wp * wy;
+  e[2] = m.alpha * p[2] - T(0.5) * (wx * p[1] - wy * p[0]) + wp * wz;
   e[3] = wx; e[4] = wy; e[5] = wz;
+}
+
+template <typename T>
+GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
+  Log6Mid<T> m;
+  log6_pre(R, m);
+  log6_post(m, p, e);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -441,22 +469,29 @@ GIK_HD void hook_target(const ArmConst<T>& ac, const T (&cube)[12], T (&tgt)[12]
   }
 }
 
-// e = log6(hand^-1 * target), hand^-1 = (B, b)
+// e = log6(hand^-1 * target), hand^-1 = (B, b); in two halves (see log6_pre / log6_post)
 template <typename T>
-GIK_HD void hand_error(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], T (&e)[6]) {
-  T R[9], p[3];
+struct ErrMid { Log6Mid<T> m; T p[3]; };
+template <>
+struct ErrMid<F2> { Log6Mid<float> ml, mr; float pl[3], pr[3]; };
+
+template <typename T>
+GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], ErrMid<T>& em) {
+  T R[9];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       R[3 * r + c] = B[3 * r] * tgt[c] + B[3 * r + 1] * tgt[3 + c] + B[3 * r + 2] * tgt[6 + c];
-    p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
+    em.p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
   }
-  log6(R, p, e);
+  log6_pre(R, em.m);
 }
+template <typename T>
+GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post(em.m, em.p, e); }
 
 // both hands at once: the products are packed, log6 (branches, transcendental functions) runs per half
-GIK_HD void hand_error(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], F2 (&e)[6]) {
+GIK_HD void hand_error_pre(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], ErrMid<F2>& em) {
   F2 R[9], p[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -465,13 +500,18 @@ GIK_HD void hand_error(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], 
       R[3 * r + c] = B[3 * r] * tgt[c] + B[3 * r + 1] * tgt[3 + c] + B[3 * r + 2] * tgt[6 + c];
     p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
   }
-  float Rl[9], Rr[9], pl[3], pr[3], el[6], er[6];
+  float Rl[9], Rr[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) { Rl[i] = R[i].x; Rr[i] = R[i].y; }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { pl[i] = p[i].x; pr[i] = p[i].y; }
-  log6(Rl, pl, el);
-  log6(Rr, pr, er);
+  for (int i = 0; i < 3; ++i) { em.pl[i] = p[i].x; em.pr[i] = p[i].y; }
+  log6_pre(Rl, em.ml);
+  log6_pre(Rr, em.mr);
+}
+GIK_HD void hand_error_post(const ErrMid<F2>& em, F2 (&e)[6]) {
+  float el[6], er[6];
+  log6_post(em.ml, em.pl, el);
+  log6_post(em.mr, em.pr, er);
 #pragma unroll
   for (int i = 0; i < 6; ++i) e[i] = F2(el[i], er[i]);
 }
@@ -490,13 +530,19 @@ struct HandState {
   T yf[6], zf[6];
 };
 
-template <typename T, int OFF, uint32_t TZ, bool G6 = true>
+template <typename T, int OFF, uint32_t TZ, bool G6 = true, bool LATE = false>
 GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
                         T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
   T B[9], b[3], A[6][7], e[6];
   hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
-  hand_error(B, b, tgt, e);
-  resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
+  // LATE: the error's branch (log6_post) comes after the Cholesky factorisation, so the straight-line part of log6 (a
+  // chain of dependent MUFU results) and the Gram / Cholesky arithmetic are one basic block the scheduler can interleave
+  ErrMid<T> em;
+  hand_error_pre(B, b, tgt, em);
+  if constexpr (!LATE) {
+    hand_error_post(em, e);
+    resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
+  }
 
   // G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle.  Two structural facts of the compiled chain save 30 of the
   // 126 products: the tip joint's column is constant, so its outer product comes from the table (ac.g6; G6 = false
@@ -542,6 +588,10 @@ GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (
       for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
       L[i][j] = v * hs.inv[j];
     }
+  }
+  if constexpr (LATE) {
+    hand_error_post(em, e);
+    resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
   }
   // forward substitution of both right-hand sides: e and the chest column c = A[:,0]
 #pragma unroll
@@ -597,8 +647,8 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
   T SyL, SzL, SyR, SzR;
   // the fp64 lane kernel keeps the tip products so that it stays bit-identical to the fp64 pair kernel (the default)
   constexpr bool G6 = sizeof(T) == 4;
-  hand_phase1<T, 0, TZ, G6>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
-  hand_phase1<T, 6, TZ, G6>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
+  hand_phase1<T, 0, TZ, G6, GIK_LATE_LANE>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
+  hand_phase1<T, 6, TZ, G6, GIK_LATE_LANE>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
   const T kappa = chest_rate(SyL, SzL, SyR, SzR);
   dq[0] = kappa;
   T dL[6], dR[6];
@@ -635,7 +685,7 @@ GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[
   }
   HandState<F2> hs;
   F2 Sy, Sz, r2;
-  hand_phase1<F2, 0, TZ>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
+  hand_phase1<F2, 0, TZ, true, GIK_LATE_LANE2>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
   const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
   dq0 = kappa;
   hand_phase2(hs, F2(kappa), dq2);

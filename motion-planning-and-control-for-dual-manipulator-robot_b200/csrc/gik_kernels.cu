@@ -413,12 +413,22 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
                               // instruction count, not by latency: 8, 9, 10, 11, 12 warps / SM all measure 9.2-9.5 M solves/s
                               // (2^20 problems), 14 and 16 warps (144 / 128 registers + spills) 9.1 / 8.9 M
 #endif
-template <typename T> struct LaunchPair;
-template <> struct LaunchPair<float>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
-template <> struct LaunchPair<double> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64; };
+#ifndef GIK_MINB_PAIR_F64_HOIST
+#define GIK_MINB_PAIR_F64_HOIST 1   // latency-bound launches only (<= one warp per SM sub-partition): registers are free
+#endif
+template <typename T, bool HOIST> struct LaunchPair;
+template <bool HOIST> struct LaunchPair<float, HOIST>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
+template <> struct LaunchPair<double, false> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64; };
+template <> struct LaunchPair<double, true>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64_HOIST; };
 
-template <typename T, int MODE, uint32_t TZ>
-__global__ void __launch_bounds__(GIK_THREADS, LaunchPair<T>::kMinBlocks)
+// HOIST: the hand's constants are selected into registers once instead of being fetched by lane-indexed constant loads
+// (39 LDC + their scoreboard waits per iteration), and the tip joint's constant outer product then comes from the table
+// as in the lane kernels.  fp32: always (this kernel only serves batches too small to fill the machine -- edge chains,
+// single solves -- where the time is the LATENCY of one chain and registers are free).  fp64: only for launches of at
+// most one warp per SM sub-partition; the large-batch fp64 kernel is bound by the FP64 pipe at 168 registers and keeps
+// the constant loads.
+template <typename T, int MODE, uint32_t TZ, bool HOIST = (sizeof(T) == 4)>
+__global__ void __launch_bounds__(GIK_THREADS, (LaunchPair<T, HOIST>::kMinBlocks))
 gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int h = lane & 1;                       // hand of this lane
@@ -426,12 +436,6 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
   const int64_t n = a.n;
   const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
-  // fp32: this kernel serves batches too small to fill the machine (edge chains, single solves), where the time is the
-  // LATENCY of one chain and registers are free -- so the hand's constants are selected into registers once instead
-  // of being fetched by lane-indexed constant loads (39 LDC + their scoreboard waits per iteration), and the tip
-  // joint's constant outer product can then come from the table as in the lane kernels.  fp64 (also the large-batch
-  // kernel, bound by the FP64 pipe at 168 registers) keeps the constant loads.
-  constexpr bool HOIST = sizeof(T) == 4;
   ArmConst<T> acr;
   T lim_lo[7], lim_hi[7];
   if constexpr (HOIST) {
@@ -445,7 +449,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
 #pragma unroll
     for (int i = 0; i < 3; ++i) { acr.finv_p[i] = h ? R.finv_p[i] : L.finv_p[i]; acr.tip_lin[i] = h ? R.tip_lin[i] : L.tip_lin[i]; }
 #pragma unroll
-    for (int i = 0; i < 21; ++i) acr.g6[i] = h ? R.g6[i] : L.g6[i];
+    for (int i = 0; i < 21; ++i) acr.g6[i] = h ? R.g6[i] : L.g6[i];      // read by the fp32 instantiation only
     lim_lo[0] = tab.lo[0]; lim_hi[0] = tab.hi[0];
 #pragma unroll
     for (int k = 0; k < 6; ++k) { lim_lo[1 + k] = h ? tab.lo[7 + k] : tab.lo[1 + k]; lim_hi[1 + k] = h ? tab.hi[7 + k] : tab.hi[1 + k]; }
@@ -511,7 +515,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     HandState<T> hs;
 #pragma unroll
     for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
-    hand_phase1<T, 0, TZ, HOIST>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
+    hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4), GIK_LATE_PAIR>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);   // fp64 keeps the tip products: bit-identical to the fp64 lane kernel
     const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
     const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
     const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
@@ -764,7 +768,7 @@ int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* b
 // is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
 // params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
 template <typename T, int MODE>
-int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair) {
+int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair, bool* hoist = nullptr) {
   int64_t max_warps = 0;
   int rc;
   if constexpr (sizeof(T) == 4) {
@@ -777,7 +781,17 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_wa
   *pair = sizeof(T) == 8 || n <= 16 * max_warps;
   if (flags & GIK_F_LANE_KERNEL) *pair = false;
   if (flags & GIK_F_PAIR_KERNEL) *pair = true;
-  if (*pair) rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
+  // fp64 pair kernel with register-resident constants: launches of at most one full warp per SM sub-partition
+  const bool hz = *pair && sizeof(T) == 8 && n <= (int64_t)16 * 4 * h->sm_count;
+  if (hoist) *hoist = hz;
+  if (*pair) {
+    if constexpr (sizeof(T) == 8) {
+      rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, true>, n, 16, blocks, per_warp, nullptr)
+              : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, false>, n, 16, blocks, per_warp, nullptr);
+    } else {
+      rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
+    }
+  }
   return rc;
 }
 
@@ -791,8 +805,8 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   int blocks = 0, lanes = 32;
-  bool pair = false;
-  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair);
+  bool pair = false, hoist = false;
+  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair, &hoist);
   if (rc) return rc;
   a.lanes = lanes;
   a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
@@ -802,8 +816,18 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   const bool nx = (tab.tzero & kNextageTZ) == kNextageTZ;   // table has (at least) the Nextage zero pattern: skip those FMAs
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) {
-    if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
-    else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    if constexpr (sizeof(T) == 8) {
+      if (hoist) {
+        if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        else gik_solve_pair_kernel<T, MODE, 0, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      } else {
+        if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ, false><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        else gik_solve_pair_kernel<T, MODE, 0, false><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      }
+    } else {
+      if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    }
   } else if constexpr (sizeof(T) == 4) {
     if (prm->flags & GIK_F_SCALAR_LANE) {
       if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);

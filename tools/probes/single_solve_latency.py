@@ -1,0 +1,30 @@
+"""Latency of ONE drop-in call (config 1: the reference's own use): computeqgrasppose(q0, CUBE_PLACEMENT) in fp64 (the
+drop-in's default) and fp32, wall clock around the Python call, plus the kernel alone (CUDA events, one problem)."""
+import sys, time
+import numpy as np
+import torch
+sys.path.insert(0, '.')
+import gik_b200
+
+dev = torch.device("cuda:0")
+solver = gik_b200.GraspIK(gik_b200.nextage_table(), dev)
+cube = (np.eye(3), np.array([0.33, -0.3, 0.93]))
+q0 = np.zeros(15)
+for dtype in (torch.float64, torch.float32):
+    for _ in range(5):
+        q, ok = gik_b200.computeqgrasppose(solver, q0, None, cube, dtype=dtype, collision=None)
+    t = time.perf_counter()
+    for _ in range(50):
+        q, ok = gik_b200.computeqgrasppose(solver, q0, None, cube, dtype=dtype, collision=None)
+    wall = (time.perf_counter() - t) / 50
+    P = torch.tensor(np.concatenate([cube[0].reshape(9), cube[1]])[:, None], dtype=dtype, device=dev)
+    Q = torch.zeros((15, 1), dtype=dtype, device=dev)
+    for _ in range(5):
+        out = solver.solve_soa(Q, P)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        out = solver.solve_soa(Q, P)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{str(dtype):14s} drop-in call {wall*1e3:.3f} ms wall (success={ok}, iterations {int(out[2][0])}) | "
+          f"kernel + launch {e0.elapsed_time(e1)/50:.3f} ms for one problem")
