@@ -30,16 +30,6 @@
 #define GIK_MAX_NQ 32
 #endif
 
-#ifndef GIK_LATE_LANE
-#define GIK_LATE_LANE false
-#endif
-#ifndef GIK_LATE_LANE2
-#define GIK_LATE_LANE2 false
-#endif
-#ifndef GIK_LATE_PAIR
-#define GIK_LATE_PAIR false
-#endif
-
 namespace gik {
 
 constexpr int kActive = 13;  // chest + 6 + 6 joints that move the hands
@@ -127,16 +117,16 @@ GIK_HD double rsqrt_(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
-GIK_HD float div_(float a, float b) {
+GIK_HD float rcp_(float b) {
 #ifdef __CUDA_ARCH__
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-  return a * r;
+  return r;
 #else
-  return a / b;
+  return 1.0f / b;
 #endif
 }
-GIK_HD double div_(double a, double b) {
+GIK_HD double rcp_(double b) {
 #ifdef __CUDA_ARCH__
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
@@ -144,16 +134,23 @@ GIK_HD double div_(double a, double b) {
   double e = fma(-b, y, 1.0);
   y = fma(y, e, y);
   e = fma(-b, y, 1.0);
-  return a * fma(y, e, y);
+  return fma(y, e, y);
 #else
   // one third-order step: y (1 + e + e^2), e = 1 - b y
   const double e = fma(-b, y, 1.0);
-  return a * fma(fma(y, e, y), e, y);
+  return fma(fma(y, e, y), e, y);
 #endif
 #else
-  return a / b;
+  return 1.0 / b;
 #endif
 }
+#ifdef __CUDA_ARCH__
+GIK_HD float div_(float a, float b) { return a * rcp_(b); }
+GIK_HD double div_(double a, double b) { return a * rcp_(b); }
+#else
+GIK_HD float div_(float a, float b) { return a / b; }
+GIK_HD double div_(double a, double b) { return a / b; }
+#endif
 GIK_HD float sqrt_(float x) {
 #ifdef __CUDA_ARCH__
   float r;
@@ -384,17 +381,22 @@ GIK_HD void log6_pre(const T (&R)[9], Log6Mid<T>& m) {
   m.c = c; m.theta = theta; m.alpha = alpha; m.beta = beta;
 }
 
-template <typename T>
+// BRANCHFREE: the near-pi form is always evaluated and selected (+ ~20 instructions, no branch).  For the pair
+// kernels, whose time is the latency of one chain at <= 1 warp per SM sub-partition: the whole iteration becomes one
+// basic block, free issue slots absorb the extra instructions.  The lane kernels (bound by issue / FMA pipe) branch.
+template <typename T, bool BRANCHFREE = false>
 GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
   T wx = m.wx, wy = m.wy, wz = m.wz;
-  if (m.theta >= T(3.14159265358979323846 - 1e-2)) {
+  const bool near_pi = m.theta >= T(3.14159265358979323846 - 1e-2);
+  if (BRANCHFREE || near_pi) {
     // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
     const T cphi = -m.c;
-    const T beta = div_(m.theta * m.theta, T(1) + cphi);
+    const T beta = div_(m.theta * m.theta, BRANCHFREE ? max_(T(1) + cphi, Num<T>::kTinyS) : T(1) + cphi);
     const T t0 = (m.d0 + cphi) * beta, t1 = (m.d1 + cphi) * beta, t2 = (m.d2 + cphi) * beta;
-    wx = (m.vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
-    wy = (m.vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
-    wz = (m.vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
+    const T nx = (m.vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
+    const T ny = (m.vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
+    const T nz = (m.vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
+    wx = near_pi ? nx : wx; wy = near_pi ? ny : wy; wz = near_pi ? nz : wz;
   }
   const T wp = m.beta * (wx * p[0] + wy * p[1] + wz * p[2]);
   e[0] = m.alpha * p[0] - T(0.5) * (wy * p[2] - wz * p[1]) + wp * wx;
@@ -487,8 +489,8 @@ GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12],
   }
   log6_pre(R, em.m);
 }
-template <typename T>
-GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post(em.m, em.p, e); }
+template <typename T, bool BRANCHFREE = false>
+GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post<T, BRANCHFREE>(em.m, em.p, e); }
 
 // both hands at once: the products are packed, log6 (branches, transcendental functions) runs per half
 GIK_HD void hand_error_pre(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], ErrMid<F2>& em) {
@@ -530,27 +532,15 @@ struct HandState {
   T yf[6], zf[6];
 };
 
-template <typename T, int OFF, uint32_t TZ, bool G6 = true, bool LATE = false>
-GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
-                        T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
-  T B[9], b[3], A[6][7], e[6];
-  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
-  // LATE: the error's branch (log6_post) comes after the Cholesky factorisation, so the straight-line part of log6 (a
-  // chain of dependent MUFU results) and the Gram / Cholesky arithmetic are one basic block the scheduler can interleave
-  ErrMid<T> em;
-  hand_error_pre(B, b, tgt, em);
-  if constexpr (!LATE) {
-    hand_error_post(em, e);
-    resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
-  }
-
-  // G = sum_k A[:,k] A[:,k]^T + lambda I, lower triangle.  Two structural facts of the compiled chain save 30 of the
-  // 126 products: the tip joint's column is constant, so its outer product comes from the table (ac.g6; G6 = false
-  // keeps the products -- the pair kernels read their arm constants by lane-dependent constant loads, where 21 more
-  // loads cost a latency-bound chain more than 21 multiplies: config 4 measured 45.1 ms with the table against 40.3); and chain
-  // joints 2 and 3 turn about the same axis with a rotation-free placement between them, so their angular parts
-  // A[3..5][2] and A[3..5][3] are the same values -- the angular-angular block takes 2 a a^T once and the
-  // angular-linear block takes a (l_2 + l_3)^T.
+// G = A A^T + lambda I (arm block, lower triangle) and its Cholesky factor into hs.L / hs.inv.
+// Two structural facts of the compiled chain save 30 of the 126 Gram products: the tip joint's column is constant, so
+// its outer product comes from the table (ac.g6; G6 = false keeps the products -- fp64, where the lane and pair
+// kernels stay bit-identical, and callers whose constants are lane-indexed constant loads: config 4 measured 45.1 ms
+// with the table against 40.3 before the pair kernel kept its constants in registers); and chain joints 2 and 3 turn
+// about the same axis with a rotation-free placement between them, so their angular parts A[3..5][2] and A[3..5][3]
+// are the same values -- the angular-angular block takes 2 a a^T once and the angular-linear block a (l_2 + l_3)^T.
+template <typename T, bool G6>
+GIK_HD void gram_cholesky(const ArmConst<T>& ac, const T (&A)[6][7], T lambda, HandState<T>& hs) {
   static_assert(chain_axis(2) == chain_axis(3), "parallel consecutive axes assumed by the Gram shortcut");
   T (&L)[6][6] = hs.L;
   T l23[3], a2[3];
@@ -589,16 +579,24 @@ GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (
       L[i][j] = v * hs.inv[j];
     }
   }
-  if constexpr (LATE) {
-    hand_error_post(em, e);
-    resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
-  }
+}
+
+template <typename T, int OFF, uint32_t TZ, bool G6 = true>
+GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
+                        T lambda, HandState<T>& hs, T& Sy, T& Sz, T& resid2) {
+  T B[9], b[3], A[6][7], e[6];
+  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
+  ErrMid<T> em;
+  hand_error_pre(B, b, tgt, em);
+  hand_error_post(em, e);
+  resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
+  gram_cholesky<T, G6>(ac, A, lambda, hs);
   // forward substitution of both right-hand sides: e and the chest column c = A[:,0]
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     T a = e[j], cc = A[j][0];
 #pragma unroll
-    for (int k = 0; k < j; ++k) { a -= L[j][k] * hs.yf[k]; cc -= L[j][k] * hs.zf[k]; }
+    for (int k = 0; k < j; ++k) { a -= hs.L[j][k] * hs.yf[k]; cc -= hs.L[j][k] * hs.zf[k]; }
     hs.yf[j] = a * hs.inv[j]; hs.zf[j] = cc * hs.inv[j];
   }
   Sy = hs.zf[0] * hs.yf[0]; Sz = hs.zf[0] * hs.zf[0];
@@ -608,6 +606,49 @@ GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int k = 0; k < 6; ++k) hs.A[i][k] = A[i][k + 1];
+}
+
+// Phase 1 in two steps for the pair kernels (the SAME operations on the same values as hand_phase1, ordered for the
+// latency of one chain): 1a ends with Sz = c.G^-1 c, which does not depend on the error, so the cross-lane exchange
+// of Sz and the reciprocal of 1 + Sz_L + Sz_R overlap with 1b (the error's assembly, the forward substitution of e).
+template <typename T, int OFF, uint32_t TZ, bool G6>
+GIK_HD void hand_phase1a(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
+                         T lambda, HandState<T>& hs, ErrMid<T>& em, T& Sz) {
+  T B[9], b[3], A[6][7];
+  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
+  hand_error_pre(B, b, tgt, em);
+  gram_cholesky<T, G6>(ac, A, lambda, hs);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    T cc = A[j][0];
+#pragma unroll
+    for (int k = 0; k < j; ++k) cc -= hs.L[j][k] * hs.zf[k];
+    hs.zf[j] = cc * hs.inv[j];
+  }
+  Sz = hs.zf[0] * hs.zf[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) Sz += hs.zf[i] * hs.zf[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hs.A[i][k] = A[i][k + 1];
+}
+
+template <typename T, bool BRANCHFREE>
+GIK_HD void hand_phase1b(HandState<T>& hs, const ErrMid<T>& em, T& Sy, T& resid2) {
+  T e[6];
+  hand_error_post<T, BRANCHFREE>(em, e);
+  resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    T a = e[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) a -= hs.L[j][k] * hs.yf[k];
+    hs.yf[j] = a * hs.inv[j];
+  }
+  Sy = hs.zf[0] * hs.yf[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) Sy += hs.zf[i] * hs.yf[i];
 }
 
 template <typename T>
@@ -647,8 +688,8 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
   T SyL, SzL, SyR, SzR;
   // the fp64 lane kernel keeps the tip products so that it stays bit-identical to the fp64 pair kernel (the default)
   constexpr bool G6 = sizeof(T) == 4;
-  hand_phase1<T, 0, TZ, G6, GIK_LATE_LANE>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
-  hand_phase1<T, 6, TZ, G6, GIK_LATE_LANE>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
+  hand_phase1<T, 0, TZ, G6>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
+  hand_phase1<T, 6, TZ, G6>(tab.arm[1], cs, sn, tgt[1], lambda, hR, SyR, SzR, resid2R);
   const T kappa = chest_rate(SyL, SzL, SyR, SzR);
   dq[0] = kappa;
   T dL[6], dR[6];
@@ -685,7 +726,7 @@ GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[
   }
   HandState<F2> hs;
   F2 Sy, Sz, r2;
-  hand_phase1<F2, 0, TZ, true, GIK_LATE_LANE2>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
+  hand_phase1<F2, 0, TZ, true>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
   const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
   dq0 = kappa;
   hand_phase2(hs, F2(kappa), dq2);
