@@ -351,9 +351,11 @@ GIK_HD void sincos_(double x, double& s, double& c) {
 // inverse_geometry.py:66-67); theta is taken as atan2(|vee(R - R^T)|/2, (tr R - 1)/2), which equals
 // acos((tr R - 1)/2) for a rotation matrix but stays accurate in fp32 near theta = 0.
 // ------------------------------------------------------------------------------------------------------
-// The function is split in two so that a caller can put independent work between the halves: log6_pre is straight-line
-// code (theta, the common-case w = theta/(2 sin theta) vee(R - R^T), alpha, beta -- a chain of dependent MUFU results),
-// log6_post holds the one data-dependent branch (pinocchio's form near theta = pi, rare) and the assembly of [v; w].
+// In two functions: log6_pre is straight-line code (theta, the common-case w = theta/(2 sin theta) vee(R - R^T), alpha,
+// beta -- a chain of dependent MUFU results), log6_post holds the one data-dependent branch (pinocchio's form near
+// theta = pi, rare) and the assembly of [v; w].  (Written this way to try orderings that put independent work between
+// the halves; none of them paid -- DESIGN.md "Tried and dropped" -- but the split itself measured 5 % faster on the
+// edge projection and is kept.)
 template <typename T>
 struct Log6Mid { T vx, vy, vz, d0, d1, d2, c, theta, wx, wy, wz, alpha, beta; };
 
@@ -381,22 +383,17 @@ GIK_HD void log6_pre(const T (&R)[9], Log6Mid<T>& m) {
   m.c = c; m.theta = theta; m.alpha = alpha; m.beta = beta;
 }
 
-// BRANCHFREE: the near-pi form is always evaluated and selected (+ ~20 instructions, no branch).  For the pair
-// kernels, whose time is the latency of one chain at <= 1 warp per SM sub-partition: the whole iteration becomes one
-// basic block, free issue slots absorb the extra instructions.  The lane kernels (bound by issue / FMA pipe) branch.
-template <typename T, bool BRANCHFREE = false>
+template <typename T>
 GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
   T wx = m.wx, wy = m.wy, wz = m.wz;
-  const bool near_pi = m.theta >= T(3.14159265358979323846 - 1e-2);
-  if (BRANCHFREE || near_pi) {
+  if (m.theta >= T(3.14159265358979323846 - 1e-2)) {
     // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
     const T cphi = -m.c;
-    const T beta = div_(m.theta * m.theta, BRANCHFREE ? max_(T(1) + cphi, Num<T>::kTinyS) : T(1) + cphi);
+    const T beta = div_(m.theta * m.theta, T(1) + cphi);
     const T t0 = (m.d0 + cphi) * beta, t1 = (m.d1 + cphi) * beta, t2 = (m.d2 + cphi) * beta;
-    const T nx = (m.vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
-    const T ny = (m.vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
-    const T nz = (m.vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
-    wx = near_pi ? nx : wx; wy = near_pi ? ny : wy; wz = near_pi ? nz : wz;
+    wx = (m.vx > T(0) ? T(1) : T(-1)) * (t0 > T(0) ? sqrt_(t0) : T(0));
+    wy = (m.vy > T(0) ? T(1) : T(-1)) * (t1 > T(0) ? sqrt_(t1) : T(0));
+    wz = (m.vz > T(0) ? T(1) : T(-1)) * (t2 > T(0) ? sqrt_(t2) : T(0));
   }
   const T wp = m.beta * (wx * p[0] + wy * p[1] + wz * p[2]);
   e[0] = m.alpha * p[0] - T(0.5) * (wy * p[2] - wz * p[1]) + wp * wx;
@@ -489,8 +486,8 @@ GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12],
   }
   log6_pre(R, em.m);
 }
-template <typename T, bool BRANCHFREE = false>
-GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post<T, BRANCHFREE>(em.m, em.p, e); }
+template <typename T>
+GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post(em.m, em.p, e); }
 
 // both hands at once: the products are packed, log6 (branches, transcendental functions) runs per half
 GIK_HD void hand_error_pre(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], ErrMid<F2>& em) {
@@ -606,49 +603,6 @@ GIK_HD void hand_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int k = 0; k < 6; ++k) hs.A[i][k] = A[i][k + 1];
-}
-
-// Phase 1 in two steps for the pair kernels (the SAME operations on the same values as hand_phase1, ordered for the
-// latency of one chain): 1a ends with Sz = c.G^-1 c, which does not depend on the error, so the cross-lane exchange
-// of Sz and the reciprocal of 1 + Sz_L + Sz_R overlap with 1b (the error's assembly, the forward substitution of e).
-template <typename T, int OFF, uint32_t TZ, bool G6>
-GIK_HD void hand_phase1a(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
-                         T lambda, HandState<T>& hs, ErrMid<T>& em, T& Sz) {
-  T B[9], b[3], A[6][7];
-  hand_chain<T, OFF, TZ>(ac, cs, sn, B, b, A);
-  hand_error_pre(B, b, tgt, em);
-  gram_cholesky<T, G6>(ac, A, lambda, hs);
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    T cc = A[j][0];
-#pragma unroll
-    for (int k = 0; k < j; ++k) cc -= hs.L[j][k] * hs.zf[k];
-    hs.zf[j] = cc * hs.inv[j];
-  }
-  Sz = hs.zf[0] * hs.zf[0];
-#pragma unroll
-  for (int i = 1; i < 6; ++i) Sz += hs.zf[i] * hs.zf[i];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hs.A[i][k] = A[i][k + 1];
-}
-
-template <typename T, bool BRANCHFREE>
-GIK_HD void hand_phase1b(HandState<T>& hs, const ErrMid<T>& em, T& Sy, T& resid2) {
-  T e[6];
-  hand_error_post<T, BRANCHFREE>(em, e);
-  resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];   // ||e||^2
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    T a = e[j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) a -= hs.L[j][k] * hs.yf[k];
-    hs.yf[j] = a * hs.inv[j];
-  }
-  Sy = hs.zf[0] * hs.yf[0];
-#pragma unroll
-  for (int i = 1; i < 6; ++i) Sy += hs.zf[i] * hs.yf[i];
 }
 
 template <typename T>

@@ -413,12 +413,6 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
                               // instruction count, not by latency: 8, 9, 10, 11, 12 warps / SM all measure 9.2-9.5 M solves/s
                               // (2^20 problems), 14 and 16 warps (144 / 128 registers + spills) 9.1 / 8.9 M
 #endif
-#ifndef GIK_PAIR_SPLIT
-#define GIK_PAIR_SPLIT false
-#endif
-#ifndef GIK_PAIR_BRANCHFREE
-#define GIK_PAIR_BRANCHFREE false
-#endif
 #ifndef GIK_MINB_PAIR_F64_HOIST
 #define GIK_MINB_PAIR_F64_HOIST 1   // latency-bound launches only (<= one warp per SM sub-partition): registers are free
 #endif
@@ -527,29 +521,15 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     if ((!GATED || refill) && exhausted && !__any_sync(0xffffffffu, active)) break;
 
     // ---------------- one descent iteration: this lane's hand ----------------
-    // Sz = c.G^-1 c does not depend on the error: its exchange and the reciprocal of the Sherman-Morrison denominator
-    // are issued before the error is assembled (phase 1b), off the critical path of the iteration.
     T cs[kActive], sn[kActive], Sy, Sz, r, dqa[6];
     HandState<T> hs;
-    ErrMid<T> em;
 #pragma unroll
     for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
     // (fp64 keeps the tip products in the Gram matrix: bit-identical to the fp64 lane kernel)
-    T kappa, r_o;
-    if constexpr (HOIST && GIK_PAIR_SPLIT) {      // early Sz exchange (+ optionally branch-free log6): measured slower, see DESIGN.md
-      hand_phase1a<T, 0, TZ, (sizeof(T) == 4)>(acl, cs, sn, tgt, a.lambda, hs, em, Sz);
-      const T Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
-      const T rden = rcp_(T(1) + (h ? Sz_o + Sz : Sz + Sz_o));           // 1 / (1 + Sz_L + Sz_R), as chest_rate
-      hand_phase1b<T, GIK_PAIR_BRANCHFREE>(hs, em, Sy, r);
-      const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1);
-      r_o = __shfl_xor_sync(0xffffffffu, r, 1);
-      kappa = (h ? Sy_o + Sy : Sy + Sy_o) * rden;
-    } else {
-      hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
-      const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
-      r_o = __shfl_xor_sync(0xffffffffu, r, 1);
-      kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
-    }
+    hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
+    const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
+    const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
+    const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
     hand_phase2(hs, kappa, dqa);
     const T rL = h ? r_o : r, rR = h ? r : r_o;
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
