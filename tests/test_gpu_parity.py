@@ -500,3 +500,31 @@ def test_early_stop_preset_keeps_flags_and_converged_q(solver):
         assert (b[2][~ok] < 1000).float().mean() > 0.95                  # failures stop early ...
         assert b[2].sum().item() < 0.85 * a[2].sum().item()              # ... which saves iterations
         assert (b[2][~ok] >= 127).all() and torch.isfinite(b[0]).all()
+
+
+def test_fp64_large_batch_instantiation_equals_lane_kernel(solver):
+    # fp64 launches of more than one warp per SM sub-partition (> 16 * 4 * SMs problems) use the pair kernel's
+    # large-batch instantiation (constant loads, queue check gated behind a warp vote) instead of the register-resident
+    # one the small tests above exercise; both must reproduce the fp64 lane kernel bit for bit -- batch and edge mode,
+    # including edges with nothing to march, which leave a lane pair idle while the queue still has work.
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 16 * 4 * sms + 517
+    assert solver.kernel_name(n, torch.float64) == "gik_solve_pair_kernel<double>"
+    P = _t(make_poses(n, 71)).t().contiguous()
+    q0 = torch.zeros((15, n), dtype=torch.float64, device="cuda:0")
+    a = solver.solve_soa(q0, P)
+    b = solver.solve_soa(q0, P, kernel="lane")
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    small = solver.solve_soa(q0[:, :1000].contiguous(), P[:, :1000].contiguous())   # register-resident form
+    assert torch.equal(small[0], a[0][:, :1000]) and torch.equal(small[2], a[2][:1000])
+    # edge mode
+    E, S = n, 3
+    A = make_poses(E, 72, "sampler"); B = A.copy(); B[:, 9:] += np.random.default_rng(5).uniform(-0.03, 0.03, size=(E, 3))
+    qs = torch.zeros((15, E), dtype=torch.float64, device="cuda:0")
+    ns = torch.from_numpy(np.random.default_rng(6).integers(0, S + 1, size=E).astype(np.int32)).to("cuda:0")
+    args = (qs, _t(A).t().contiguous(), _t(B).t().contiguous(), ns, S)
+    pa = solver.project_edges_soa(*args)
+    pb = solver.project_edges_soa(*args, kernel="lane")
+    assert torch.equal(pa[1], pb[1]) and torch.equal(pa[2], pb[2]) and torch.equal(pa[0], pb[0])
+    assert (pa[1][ns == 0] == 0).all() and (pa[1] == ns).float().mean() > 0.2      # and many edges march to their end
