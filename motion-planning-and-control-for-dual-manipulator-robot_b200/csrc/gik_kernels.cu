@@ -400,8 +400,10 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 // warp shuffles per iteration (the two Sherman-Morrison scalars and the residual).  Per-warp instruction count per
 // iteration is about half of the lane kernel's, so this is the kernel for batches too small to give every lane of
 // the machine its own problem (path.py edge projection: 4096 chains; the single-solve drop-in) -- there the cost
-// is issue slots per chain-iteration, not lane occupancy.  Same operations on the same values as the lane kernel.
-// Arm constants are lane dependent: they come from the kernel-parameter table by indexed constant loads.
+// is the latency of one chain-iteration, not lane occupancy -- and for every fp64 batch (half the live state per
+// lane).  Same operations on the same values as the lane kernel.  Arm constants are lane dependent (hand = lane & 1):
+// register-resident in the latency-bound instantiations, lane-indexed constant loads in the large-batch fp64 one
+// (HOIST below).
 // ========================================================================================================
 #ifndef GIK_MINB_PAIR_F32
 #define GIK_MINB_PAIR_F32 3   // 165 registers: the hand's constants live in registers (HOIST below).  Measured against the
