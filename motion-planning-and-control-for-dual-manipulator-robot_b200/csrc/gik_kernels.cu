@@ -415,6 +415,10 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
                               // instruction count, not by latency: 8, 9, 10, 11, 12 warps / SM all measure 9.2-9.5 M solves/s
                               // (2^20 problems), 14 and 16 warps (144 / 128 registers + spills) 9.1 / 8.9 M
 #endif
+#ifndef GIK_PAIR_INNER
+#define GIK_PAIR_INNER true   // measured against the single-loop form: config 4 29.97 -> 27.12 ms, 2 Ki fp32 problems 0.64 -> 0.58 ms,
+                              // 16 Ki 1.00 -> 0.93 ms, fp64 small batches unchanged
+#endif
 #ifndef GIK_MINB_PAIR_F64_HOIST
 #define GIK_MINB_PAIR_F64_HOIST 1   // latency-bound launches only (<= one warp per SM sub-partition): registers are free
 #endif
@@ -476,6 +480,9 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   // latency-bound instantiations run the queue check every trip: gating it measured 6 % SLOWER on config 4 (30.0 ->
   // 31.8 ms; code layout of a 11 KB loop running from the instruction cache with one warp per sub-partition).
   constexpr bool GATED = !HOIST;
+  constexpr bool INNER = HOIST && GIK_PAIR_INNER;
+  const T dt = a.dt, eps2 = a.eps2, lambda = a.lambda;
+  const int max_iters = a.max_iters;
   bool refill = true;
   for (;;) {
     const unsigned need = ((GATED && !refill) || exhausted) ? 0u : (__ballot_sync(0xffffffffu, enabled && !active) & 0x55555555u);
@@ -520,43 +527,61 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       // an edge with nothing to march leaves its pair idle although the queue has more: come back next trip
       if (GATED && MODE == MODE_EDGES) again = !exhausted && __any_sync(0xffffffffu, enabled && !active);
     }
-    if ((!GATED || refill) && exhausted && !__any_sync(0xffffffffu, active)) break;
+    if constexpr (INNER) {
+      if (!__any_sync(0xffffffffu, active)) {
+        if (exhausted) break;
+        continue;                                // (edges with nothing to march) back to the queue
+      }
+    } else {
+      if ((!GATED || refill) && exhausted && !__any_sync(0xffffffffu, active)) break;
+    }
 
     // ---------------- one descent iteration: this lane's hand ----------------
-    T cs[kActive], sn[kActive], Sy, Sz, r, dqa[6];
-    HandState<T> hs;
+    // INNER (the latency-bound instantiations): the iteration repeats in a loop of its own until an active pair
+    // finishes -- its trip is the arithmetic, one vote and the back edge; the queue / store logic above and below runs
+    // only then.  Stall samples of the single-loop form put 14 % of a lone chain's time on its four branches per trip
+    // (branch_resolving + instruction fetch at the targets).  [The same idea as a FLAG in the single loop measured
+    // slower, 30.0 -> 31.8 ms; as a loop it is 27.1 ms.]
+    bool ok, done;
+    T r;
+    for (;;) {
+      T cs[kActive], sn[kActive], Sy, Sz, dqa[6];
+      HandState<T> hs;
 #pragma unroll
-    for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
-    // (fp64 keeps the tip products in the Gram matrix: bit-identical to the fp64 lane kernel)
-    hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, a.lambda, hs, Sy, Sz, r);
-    const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
-    const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
-    const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
-    hand_phase2(hs, kappa, dqa);
-    const T rL = h ? r_o : r, rR = h ? r : r_o;
-    const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
-    bool stalled = false;
-    if (a.early_stop && (it & 63) == 63) {
-      const T rs = rL + rR;
-      stalled = rs > T(0.9) * r_mark;
-      r_mark = rs;
-    }
-    const bool done = ok || (it >= a.max_iters) || stalled;
-    if constexpr (GATED) refill = __any_sync(0xffffffffu, done && active) || again;
-
-    if (!done) {
-      if constexpr (HOIST) {
-        q[0] = min_(max_(lim_lo[0], q[0] + a.dt * kappa), lim_hi[0]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) q[1 + k] = min_(max_(lim_lo[1 + k], q[1 + k] + a.dt * dqa[k]), lim_hi[1 + k]);
-      } else {
-        q[0] = min_(max_(tab.lo[0], q[0] + a.dt * kappa), tab.hi[0]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + a.dt * dqa[k]), tab.hi[off + k]);
+      for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
+      // (fp64 keeps the tip products in the Gram matrix: bit-identical to the fp64 lane kernel)
+      hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, lambda, hs, Sy, Sz, r);
+      const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
+      const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
+      const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
+      hand_phase2(hs, kappa, dqa);
+      const T rL = h ? r_o : r, rR = h ? r : r_o;
+      ok = (rL < eps2) && (rR < eps2) && (it < max_iters);
+      bool stalled = false;
+      if (a.early_stop && (it & 63) == 63) {
+        const T rs = rL + rR;
+        stalled = rs > T(0.9) * r_mark;
+        r_mark = rs;
       }
-      ++it;
-    } else if (active) {
+      done = ok || (it >= max_iters) || stalled;
+      if constexpr (GATED) refill = __any_sync(0xffffffffu, done && active) || again;
+      if (!done) {
+        if constexpr (HOIST) {
+          q[0] = min_(max_(lim_lo[0], q[0] + dt * kappa), lim_hi[0]);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) q[1 + k] = min_(max_(lim_lo[1 + k], q[1 + k] + dt * dqa[k]), lim_hi[1 + k]);
+        } else {
+          q[0] = min_(max_(tab.lo[0], q[0] + dt * kappa), tab.hi[0]);
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            q[1 + k] = min_(max_(tab.lo[off + k], q[1 + k] + dt * dqa[k]), tab.hi[off + k]);
+        }
+        ++it;
+      }
+      if (!INNER) break;
+      if (__any_sync(0xffffffffu, done && active)) break;
+    }
+    if (done && active) {
       const bool batch = (MODE == MODE_BATCH);
       if (!batch) it_total += it;
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
