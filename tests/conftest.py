@@ -98,6 +98,14 @@ class HostSim:
         return q.T, c.astype(bool), it, r.T
 
 
+    def atan2_pos(self, y, x, dtype):
+        y = np.ascontiguousarray(np.asarray(y, dtype)); x = np.ascontiguousarray(np.asarray(x, dtype))
+        out = np.zeros_like(y)
+        f = self.lib.hostsim_atan2_pos_f32 if dtype == np.float32 else self.lib.hostsim_atan2_pos_f64
+        f.restype = None
+        f(ctypes.c_int64(y.size), self._p(y), self._p(x), self._p(out))
+        return out
+
     def collide(self, tc, sc, q_rows, cube_rows, dtype, mode=0, margin=0.0):
         """mode 0: collision(q); 1: some table/obstacle pair closer than `margin`; 2: cube vs table/obstacle."""
         f = self.lib.hostsim_collide_f32 if dtype == np.float32 else self.lib.hostsim_collide_f64

@@ -134,6 +134,13 @@ static int pair_impl(int ta, const double* Ra, const double* pa, const double* s
 }
 
 extern "C" {
+// scalar functions of gik_core.cuh whose host and device forms share their code (polynomial atan2, log6)
+void hostsim_atan2_pos_f64(int64_t n, const double* y, const double* x, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = atan2_pos(y[i], x[i]);
+}
+void hostsim_atan2_pos_f32(int64_t n, const float* y, const float* x, float* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = atan2_pos(y[i], x[i]);
+}
 int hostsim_collide_f32(const gik_table_t* t, const gik_scene_t* s, int64_t n, const float* q, const float* cube, int list, double m, uint8_t* o) { return collide_impl<float>(t, s, n, q, cube, list, m, o); }
 int hostsim_collide_f64(const gik_table_t* t, const gik_scene_t* s, int64_t n, const double* q, const double* cube, int list, double m, uint8_t* o) { return collide_impl<double>(t, s, n, q, cube, list, m, o); }
 int hostsim_pair_f32(int ta, const double* Ra, const double* pa, const double* sa, int tb, const double* Rb, const double* pb, const double* sb, double m) { return pair_impl<float>(ta, Ra, pa, sa, tb, Rb, pb, sb, m); }
