@@ -485,9 +485,11 @@ def run_b200(args):
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    traffic = None
+    traffic = pipe_busy = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.dtype) if args.config == 2 else None
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(args.dtype) if args.config == 2 else None
+        pipe_busy = tj.get("pipe_busy", {}).get(args.dtype) if args.config == 2 else None
     except Exception:
         pass
     roofline = {
@@ -499,6 +501,9 @@ def run_b200(args):
                        "MEASURED_PEAKS.json has no CUDA-core figure",
         "flops_per_iteration": fpi, "iterations_per_launch": iters_per_launch, "kernel_ms": kernel_ms,
         "traffic": traffic,
+        # `frac` uses the survey's ALGORITHMIC FLOP count (3117 / iteration); the kernel executes fewer (DESIGN.md
+        # "Roofline"), so frac can exceed 1.  How busy the pipe really is comes from the committed ncu capture:
+        "pipe_busy_ncu": pipe_busy,
         "hbm": {"algorithmic_bytes_per_launch": bytes_algo,
                 "achieved_gbs": bytes_algo / (kernel_ms * 1e-3) * 1e-9, "peak_gbs": hbm_peak,
                 "frac": (bytes_algo / (kernel_ms * 1e-3) * 1e-9 / hbm_peak) if hbm_peak else None},
