@@ -437,8 +437,12 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 #define GIK_PAIR_INNER true   // measured against the single-loop form: config 4 29.97 -> 27.12 ms, 2 Ki fp32 problems 0.64 -> 0.58 ms,
                               // 16 Ki 1.00 -> 0.93 ms, fp64 small batches unchanged
 #endif
+#ifndef GIK_F64_HOIST_WARPS
+#define GIK_F64_HOIST_WARPS 8   // warps per SM (= its two resident blocks) up to which an fp64 launch takes the register-resident
+                                // instantiation: 12 Ki / 18 Ki problems 2.64 -> 2.47 ms against the 168-register one
+#endif
 #ifndef GIK_MINB_PAIR_F64_HOIST
-#define GIK_MINB_PAIR_F64_HOIST 1   // latency-bound launches only (<= one warp per SM sub-partition): registers are free
+#define GIK_MINB_PAIR_F64_HOIST 1   // launches of <= GIK_F64_HOIST_WARPS warps per SM only: registers are free (252 used, two blocks per SM)
 #endif
 template <typename T, bool HOIST> struct LaunchPair;
 template <bool HOIST> struct LaunchPair<float, HOIST>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
@@ -448,8 +452,8 @@ template <> struct LaunchPair<double, true>  { static constexpr int kMinBlocks =
 // HOIST: the hand's constants are selected into registers once instead of being fetched by lane-indexed constant loads
 // (39 LDC + their scoreboard waits per iteration), and the tip joint's constant outer product then comes from the table
 // as in the lane kernels.  fp32: always (this kernel only serves batches too small to fill the machine -- edge chains,
-// single solves -- where the time is the LATENCY of one chain and registers are free).  fp64: only for launches of at
-// most one warp per SM sub-partition; the large-batch fp64 kernel is bound by the FP64 pipe at 168 registers and keeps
+// single solves -- where the time is the LATENCY of one chain and registers are free).  fp64: only for launches that fit
+// its two resident blocks per SM (<= 8 warps per SM); the large-batch fp64 kernel is bound by the FP64 pipe at 168 registers and keeps
 // the constant loads.
 template <typename T, int MODE, uint32_t TZ, bool HOIST = (sizeof(T) == 4)>
 __global__ void __launch_bounds__(GIK_THREADS, (LaunchPair<T, HOIST>::kMinBlocks))
@@ -839,7 +843,7 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_wa
   if (flags & GIK_F_LANE_KERNEL) *pair = false;
   if (flags & GIK_F_PAIR_KERNEL) *pair = true;
   // fp64 pair kernel with register-resident constants: launches of at most one full warp per SM sub-partition
-  const bool hz = *pair && sizeof(T) == 8 && n <= (int64_t)16 * 4 * h->sm_count;
+  const bool hz = *pair && sizeof(T) == 8 && n <= (int64_t)16 * GIK_F64_HOIST_WARPS * h->sm_count;
   if (hoist) *hoist = hz;
   if (*pair) {
     if constexpr (sizeof(T) == 8) {

@@ -503,12 +503,12 @@ def test_early_stop_preset_keeps_flags_and_converged_q(solver):
 
 
 def test_fp64_large_batch_instantiation_equals_lane_kernel(solver):
-    # fp64 launches of more than one warp per SM sub-partition (> 16 * 4 * SMs problems) use the pair kernel's
+    # fp64 launches of more than 8 warps per SM (> 16 * 8 * SMs problems) use the pair kernel's
     # large-batch instantiation (constant loads, queue check gated behind a warp vote) instead of the register-resident
     # one the small tests above exercise; both must reproduce the fp64 lane kernel bit for bit -- batch and edge mode,
     # including edges with nothing to march, which leave a lane pair idle while the queue still has work.
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    n = 16 * 4 * sms + 517
+    n = 16 * 8 * sms + 517
     assert solver.kernel_name(n, torch.float64) == "gik_solve_pair_kernel<double>"
     P = _t(make_poses(n, 71)).t().contiguous()
     q0 = torch.zeros((15, n), dtype=torch.float64, device="cuda:0")
