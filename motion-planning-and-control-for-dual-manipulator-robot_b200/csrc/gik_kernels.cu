@@ -67,10 +67,18 @@ struct SolveArgs {
   unsigned long long* queue;  // work queue head (zeroed on the stream before the launch): next problem to hand out
 };
 
+// Problem inputs (q_init, pose, num_steps) are read with ld.global.cg (L2 only), never with the non-coherent path:
+// on the streamed host path (gik_solve_rows_*) the copy engine is still writing those staging buffers while the kernel
+// runs, and ld.global.nc (__ldg) is only defined for data that is read-only during the kernel's lifetime -- a stale L1
+// sector left by a warp that read the last row of one slab could otherwise serve the first row of the next slab.
+// Every input is read exactly once per problem, so bypassing L1 costs nothing.
+template <typename U>
+__device__ __forceinline__ U ld_in(const U* p) { return __ldcg(p); }
+
 template <typename T>
 __device__ __forceinline__ void load_cube(const T* pose, int64_t sc, int64_t si, int64_t idx, T (&cube)[12]) {
 #pragma unroll
-  for (int c = 0; c < 12; ++c) cube[c] = __ldg(pose + (int64_t)c * sc + idx * si);
+  for (int c = 0; c < 12; ++c) cube[c] = ld_in(pose + (int64_t)c * sc + idx * si);
 }
 
 // the problems a refill is about to take must be resident (streamed input); no-op for device-resident batches
@@ -79,6 +87,7 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
   if (a.ready) {
     if (upto > (unsigned long long)a.n) upto = (unsigned long long)a.n;
     while (*(const volatile unsigned long long*)a.ready < upto) __nanosleep(200);
+    __threadfence();   // acquire: the slab's rows are read only after the counter that publishes them
   }
 }
 
@@ -128,11 +137,11 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           it = 0;
           r_mark = T(3.0e38);
 #pragma unroll
-          for (int i = 0; i < kActive; ++i) q[i] = __ldg(a.q_init + (int64_t)tab.act_q[i] * a.q_sc + idx * a.q_si);
+          for (int i = 0; i < kActive; ++i) q[i] = ld_in(a.q_init + (int64_t)tab.act_q[i] * a.q_sc + idx * a.q_si);
           T cube[12];
           load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
-            nsteps = __ldg(a.num_steps + idx);
+            nsteps = ld_in(a.num_steps + idx);
             step = 1;
             it_total = 0;
             T cb[12], xi[6], ca[12];
@@ -179,7 +188,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_sc + col * a.out_si] = q[i];
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
-            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
+            T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
             qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
@@ -197,7 +206,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
-            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
+            T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
             dst[(int64_t)j * n + idx] = v;
           }
@@ -297,14 +306,14 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
           active = true;
           it = 0;
           r_mark = T(3.0e38);
-          q0 = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
+          q0 = ld_in(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
           for (int k = 0; k < 6; ++k)
-            q2[k] = F2(__ldg(a.q_init + (int64_t)tab.act_q[1 + k] * a.q_sc + idx * a.q_si), __ldg(a.q_init + (int64_t)tab.act_q[7 + k] * a.q_sc + idx * a.q_si));
+            q2[k] = F2(ld_in(a.q_init + (int64_t)tab.act_q[1 + k] * a.q_sc + idx * a.q_si), ld_in(a.q_init + (int64_t)tab.act_q[7 + k] * a.q_sc + idx * a.q_si));
           T cube[12];
           load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
-            nsteps = __ldg(a.num_steps + idx);
+            nsteps = ld_in(a.num_steps + idx);
             step = 1;
             it_total = 0;
             T cb[12], xi[6], ca[12];
@@ -368,7 +377,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
           store_q(qo, a.out_sc, a.out_si, col);
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
-            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
+            T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
             qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
@@ -385,7 +394,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
-            T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
+            T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
             dst[(int64_t)j * n + idx] = v;
           }
@@ -523,13 +532,13 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
           active = true;
           it = 0;
           r_mark = T(3.0e38);
-          q[0] = __ldg(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
+          q[0] = ld_in(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) q[1 + k] = __ldg(a.q_init + (int64_t)tab.act_q[off + k] * a.q_sc + idx * a.q_si);
+          for (int k = 0; k < 6; ++k) q[1 + k] = ld_in(a.q_init + (int64_t)tab.act_q[off + k] * a.q_sc + idx * a.q_si);
           T cube[12];
           load_cube(a.pose, a.pose_sc, a.pose_si, idx, cube);
           if (MODE == MODE_EDGES) {
-            nsteps = __ldg(a.num_steps + idx);
+            nsteps = ld_in(a.num_steps + idx);
             step = 1;
             it_total = 0;
             T cb[12], xi[6], ca[12];
@@ -618,7 +627,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
             dst[(int64_t)tab.act_q[0] * ld + col * cs_] = q[0];
             for (int p = 0; p < tab.n_passive; ++p) {
               const int j = tab.passive_q[p];
-              T v = __ldg(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
+              T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
               if (moved) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
               dst[(int64_t)j * ld + col * cs_] = v;
             }

@@ -164,11 +164,13 @@ def computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None, *, collision=
 
 def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, eps=EPSILON, dt=DT,
                             max_iters=MAX_ITERS, damping=0.0, restarts=1, generator=None, return_info=False,
-                            collision=False, cube=None):
+                            collision=False, cube=None, out=None):
     """Batched entry point (new).  `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (Nextage).
     q_init [B,nq] or [nq]; cube_pose [B,12|4x4|7|3].  CUDA tensors in -> CUDA tensors out (q [B,nq], converged bool
-    [B][, SolveInfo]) with no host synchronisation; CPU tensors in -> CPU tensors out through the pipelined host path
-    (GraspIK.solve_host: H2D, solve and D2H of successive slabs overlap).  With restarts=R > 1, restart 0 starts from q_init and restarts
+    [B][, SolveInfo]) with no host synchronisation; CPU tensors / numpy arrays in -> CPU tensors out through the pipelined
+    host path (GraspIK.solve_host: H2D, solve and D2H overlap in one launch).  The returned host tensors are freshly
+    allocated and owned by the caller; `out=(q, converged_u8[, iters, resid])` (pinned CPU tensors) makes the host path
+    allocation-free by storing into the caller's buffers instead.  With restarts=R > 1, restart 0 starts from q_init and restarts
     1..R-1 from configurations drawn uniformly inside the joint limits; the best converged candidate (smallest
     max residual, ties -> lowest restart) is returned (BASELINE config 3).  `collision=True` makes the returned flag
     the reference's full `success` (converged and collision-free on the attached scene, with the reference's
@@ -178,10 +180,12 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
     kernel contract; `apply_collision` applies a host-side test afterwards)."""
     solver = solver_for(robot, cube)
     host_in = (not torch.is_tensor(cube_pose) or not cube_pose.is_cuda) and (not torch.is_tensor(q_init) or not q_init.is_cuda)
-    if host_in and not collision and restarts <= 1 and torch.is_tensor(cube_pose):
+    if out is not None and not (host_in and not collision and restarts <= 1):
+        raise ValueError("out= is only supported on the host path (CPU inputs, no collision term, restarts=1)")
+    if host_in and not collision and restarts <= 1:
         # CPU tensors in -> CPU (pinned) tensors out, copies pipelined with the solve (GraspIK.solve_host)
         return solver.solve_host(q_init, cube_pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
-                                 return_info=return_info)
+                                 return_info=return_info, out=out)
     if collision and restarts <= 1:
         p12 = as_pose12(cube_pose, dtype=dtype, device=solver.device)
         B = p12.shape[0]

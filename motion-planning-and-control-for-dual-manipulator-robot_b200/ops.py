@@ -4,6 +4,7 @@ current torch stream and never synchronise."""
 from __future__ import annotations
 
 import ctypes
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -417,10 +418,37 @@ def _pinned(cache, key, shape, dtype):
     return t
 
 
+def _slab_bounds(B: int, slabs: int, align: int = 32):
+    """Slab boundaries of the streamed host path: a small first slab so the kernel starts early, the rest in equal
+    parts, every interior boundary a multiple of `align` rows (rows are 60 / 48 B: a multiple of 32 rows is a multiple
+    of 128 B, so no cache line ever holds rows of two slabs)."""
+    slabs = max(1, int(slabs))
+    if slabs == 1 or B <= (1 << 16):                 # small batches: one slab, nothing to overlap
+        return [0, B]
+    first = min(B, max(1 << 16, B // 16))
+    first -= first % align
+    if first <= 0 or first >= B:
+        return [0, B]
+    bounds = [0, first]
+    for k in range(1, slabs):
+        b = first + ((B - first) * k) // (slabs - 1)
+        if k < slabs - 1:
+            b -= b % align
+        if b > bounds[-1]:
+            bounds.append(b)
+    bounds[-1] = B
+    return bounds
+
+
 def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0,
-               slabs=4, return_info=False, kernel=None):
-    """Host-buffer entry: q_init [B,nq] (or [nq]) and pose [B,12|4x4|7|3] are CPU tensors / arrays; returns CPU tensors
-    (q [B,nq], converged bool [B][, SolveInfo]) in pinned memory owned by the solver (valid until the next call).
+               slabs=4, return_info=False, kernel=None, out=None):
+    """Host-buffer entry: q_init [B,nq] (or [nq]) and pose [B,12|4x4|7|3] are CPU tensors / arrays (pageable or pinned);
+    returns CPU tensors (q [B,nq], converged bool [B][, SolveInfo]).
+
+    Ownership: by default the results are FRESH pinned tensors owned by the caller (one pinned allocation per call).
+    `out=(q [B,nq], converged uint8 [B][, iters int32 [B], resid [B,2]])` -- pinned, contiguous CPU tensors -- makes the
+    call allocation-free: the kernel stores straight into them (the zero-copy path bench.py's e2e leg uses).  The
+    device staging buffers are cached on the solver and guarded by a lock: concurrent calls on one solver serialise.
 
     ONE solve launch (gik_solve_rows_*), overlapped with its own transfers:
       * inputs: the copy engine streams the row-major host arrays into device staging buffers slab by slab on a copy
@@ -437,51 +465,68 @@ def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, m
         qi = qi.unsqueeze(0)
     if qi.shape[0] == 1 and B != 1:
         qi = qi.expand(B, self.nq)
-    cache = self.__dict__.setdefault("_host_cache", {})
-    q_in = qi if (qi.is_pinned() and qi.is_contiguous()) else _pinned(cache, "q_in", (B, self.nq), dtype).copy_(qi)
-    p_in = p12 if (p12.is_pinned() and p12.is_contiguous()) else _pinned(cache, "p_in", (B, 12), dtype).copy_(p12)
-    q_out = _pinned(cache, "q_out", (B, self.nq), dtype)
-    c_out = _pinned(cache, "c_out", (B,), torch.uint8)
-    it_out = _pinned(cache, "it_out", (B,), torch.int32) if return_info else None
-    r_out = _pinned(cache, "r_out", (B, 2), dtype) if return_info else None
+    if out is not None:
+        q_out, c_out = out[0], out[1]
+        it_out = out[2] if len(out) > 2 else None
+        r_out = out[3] if len(out) > 3 else None
+        if return_info and (it_out is None or r_out is None):
+            raise ValueError("return_info=True needs out=(q, converged, iters, resid)")
+        want = [(q_out, (B, self.nq), dtype), (c_out, (B,), torch.uint8)]
+        if it_out is not None:
+            want.append((it_out, (B,), torch.int32))
+        if r_out is not None:
+            want.append((r_out, (B, 2), dtype))
+        for t, shape, dt_ in want:
+            if tuple(t.shape) != shape or t.dtype != dt_ or not t.is_contiguous() or t.is_cuda or (B and not t.is_pinned()):
+                raise ValueError(f"out tensors must be pinned contiguous CPU tensors; expected {shape} {dt_}")
+    else:
+        q_out = torch.empty((B, self.nq), dtype=dtype).pin_memory() if B else torch.empty((0, self.nq), dtype=dtype)
+        c_out = torch.empty((B,), dtype=torch.uint8).pin_memory() if B else torch.empty((0,), dtype=torch.uint8)
+        it_out = (torch.empty((B,), dtype=torch.int32).pin_memory() if B else torch.empty((0,), dtype=torch.int32)) if return_info else None
+        r_out = (torch.empty((B, 2), dtype=dtype).pin_memory() if B else torch.empty((0, 2), dtype=dtype)) if return_info else None
     if B == 0:
         return (q_out, c_out.view(torch.bool)) + ((SolveInfo(it_out, r_out),) if return_info else ())
-    key = (B, dtype)
-    if cache.get("stage_key") != key:
-        cache["stage_key"] = key
-        cache["dq"] = torch.empty((B, self.nq), dtype=dtype, device=dev)
-        cache["dp"] = torch.empty((B, 12), dtype=dtype, device=dev)
-        cache["ready"] = torch.zeros((1,), dtype=torch.int64, device=dev)
-    dq, dp, ready = cache["dq"], cache["dp"], cache["ready"]
-    copy_stream = cache.get("copy_stream")
-    if copy_stream is None:
-        copy_stream = cache["copy_stream"] = torch.cuda.Stream(device=dev)
-    # slab boundaries: a small first slab so the kernel starts early, the rest in equal parts
-    slabs = max(1, int(slabs))
-    first = min(B, max(1 << 16, B // 16)) if slabs > 1 else B
-    bounds = [0, first] + [first + ((B - first) * k) // (slabs - 1) for k in range(1, slabs)] if slabs > 1 and first < B else [0, B]
-    marks = _pinned(cache, "marks", (len(bounds) - 1,), torch.int64)
-    marks.copy_(torch.tensor(bounds[1:], dtype=torch.int64))
-    cur = torch.cuda.current_stream(dev)
-    copy_stream.wait_stream(cur)                      # staging buffers may still be read by a previous launch
-    first_in = torch.cuda.Event()
-    with torch.cuda.stream(copy_stream):
-        ready.zero_()
-        for k in range(len(bounds) - 1):
-            lo, hi = bounds[k], bounds[k + 1]
-            dq[lo:hi].copy_(q_in[lo:hi], non_blocking=True)
-            dp[lo:hi].copy_(p_in[lo:hi], non_blocking=True)
-            ready.copy_(marks[k:k + 1], non_blocking=True)
-            if k == 0:
-                first_in.record(copy_stream)
-    cur.wait_event(first_in)
-    prm = self._params(eps, dt, max_iters, damping, kernel)
-    f = getattr(self._lib, f"gik_solve_rows_{_sfx(dtype)}")
-    _cabi.check(f(self._h, B, self._ptr(dq), self._ptr(dp), ctypes.byref(prm), self._ptr(q_out), self._ptr(c_out),
-                  self._ptr(it_out), self._ptr(r_out), self._ptr(ready), self._stream()), "gik_solve_rows")
-    self.launches += 1
-    cur.synchronize()          # results are host memory: the call returns when the kernel has stored them
-    copy_stream.synchronize()
+    lock = self.__dict__.setdefault("_host_lock", threading.Lock())
+    with lock:
+        cache = self.__dict__.setdefault("_host_cache", {})
+        # pageable inputs are staged through cached pinned buffers (a host memcpy); pinned inputs are used in place
+        q_in = qi if (qi.is_pinned() and qi.is_contiguous()) else _pinned(cache, "q_in", (B, self.nq), dtype).copy_(qi)
+        p_in = p12 if (p12.is_pinned() and p12.is_contiguous()) else _pinned(cache, "p_in", (B, 12), dtype).copy_(p12)
+        key = (B, dtype)
+        if cache.get("stage_key") != key:
+            cache["stage_key"] = key
+            cache["dq"] = torch.empty((B, self.nq), dtype=dtype, device=dev)
+            cache["dp"] = torch.empty((B, 12), dtype=dtype, device=dev)
+            cache["ready"] = torch.zeros((1,), dtype=torch.int64, device=dev)
+        dq, dp, ready = cache["dq"], cache["dp"], cache["ready"]
+        if self.__dict__.get("_poison_staging"):          # test hook: stale staging contents must never be read
+            dq.fill_(float("nan")); dp.fill_(float("nan"))
+        copy_stream = cache.get("copy_stream")
+        if copy_stream is None:
+            copy_stream = cache["copy_stream"] = torch.cuda.Stream(device=dev)
+        bounds = _slab_bounds(B, slabs)
+        marks = _pinned(cache, "marks", (len(bounds) - 1,), torch.int64)
+        marks.copy_(torch.tensor(bounds[1:], dtype=torch.int64))
+        cur = torch.cuda.current_stream(dev)
+        copy_stream.wait_stream(cur)                      # staging buffers may still be read by a previous launch
+        first_in = torch.cuda.Event()
+        with torch.cuda.stream(copy_stream):
+            ready.zero_()
+            for k in range(len(bounds) - 1):
+                lo, hi = bounds[k], bounds[k + 1]
+                dq[lo:hi].copy_(q_in[lo:hi], non_blocking=True)
+                dp[lo:hi].copy_(p_in[lo:hi], non_blocking=True)
+                ready.copy_(marks[k:k + 1], non_blocking=True)
+                if k == 0:
+                    first_in.record(copy_stream)
+        cur.wait_event(first_in)
+        prm = self._params(eps, dt, max_iters, damping, kernel)
+        f = getattr(self._lib, f"gik_solve_rows_{_sfx(dtype)}")
+        _cabi.check(f(self._h, B, self._ptr(dq), self._ptr(dp), ctypes.byref(prm), self._ptr(q_out), self._ptr(c_out),
+                      self._ptr(it_out), self._ptr(r_out), self._ptr(ready), self._stream()), "gik_solve_rows")
+        self.launches += 1
+        cur.synchronize()          # results are host memory: the call returns when the kernel has stored them
+        copy_stream.synchronize()
     return (q_out, c_out.view(torch.bool)) + ((SolveInfo(it_out, r_out),) if return_info else ())
 
 

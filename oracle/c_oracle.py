@@ -68,11 +68,13 @@ def jac(table_c, q):
     return out
 
 
-def solve(table_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0):
+def solve(table_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0, damping=0.0):
+    """damping = 0: the reference's pinv step; > 0: J^T (J J^T + damping I)^-1 e (BASELINE config 3's setting)."""
     q_init = _c(q_init); pose12 = _c(pose12); n, nq = q_init.shape
     q = np.empty((n, nq)); conv = np.empty(n, np.uint8); it = np.empty(n, np.int32); res = np.empty((n, 2))
     lib().orc_solve(ctypes.byref(table_c), ctypes.c_int64(n), _p(q_init), _p(pose12), ctypes.c_double(eps),
-                    ctypes.c_double(dt), ctypes.c_int(max_iters), ctypes.c_int(threads), _p(q), _p(conv), _p(it), _p(res))
+                    ctypes.c_double(dt), ctypes.c_int(max_iters), ctypes.c_double(damping), ctypes.c_int(threads), _p(q),
+                    _p(conv), _p(it), _p(res))
     return q, conv.astype(bool), it, res
 
 
@@ -83,13 +85,14 @@ def interpolate(A12, B12, alpha):
     return out
 
 
-def project_edges(table_c, q_start, pose_a, pose_b, num_steps, max_steps, eps=1e-3, dt=1e-2, max_iters=1000, threads=0):
+def project_edges(table_c, q_start, pose_a, pose_b, num_steps, max_steps, eps=1e-3, dt=1e-2, max_iters=1000, threads=0,
+                  damping=0.0):
     q_start = _c(q_start); pose_a = _c(pose_a); pose_b = _c(pose_b); ns = _c(num_steps, np.int32)
     n, nq = q_start.shape
     path = np.zeros((n, max_steps, nq)); nv = np.empty(n, np.int32); itt = np.empty(n, np.int32)
     lib().orc_project_edges(ctypes.byref(table_c), ctypes.c_int64(n), ctypes.c_int(max_steps), _p(q_start), _p(pose_a),
                             _p(pose_b), _p(ns), ctypes.c_double(eps), ctypes.c_double(dt), ctypes.c_int(max_iters),
-                            ctypes.c_int(threads), _p(path), _p(nv), _p(itt))
+                            ctypes.c_double(damping), ctypes.c_int(threads), _p(path), _p(nv), _p(itt))
     return path, nv, itt
 
 
@@ -109,13 +112,17 @@ def scene_distance(table_c, scene_c, q, cube_pose=None, mode=0, cull=0.0, thread
     return out
 
 
-def solve_success(table_c, scene_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0):
-    """computeqgrasppose with the collision term of the predicate (inverse_geometry.py:70, 97-98)."""
+def solve_success(table_c, scene_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0, damping=0.0,
+                  return_ever=False):
+    """computeqgrasppose with the collision term of the predicate (inverse_geometry.py:70, 97-98).
+    return_ever: also return whether both residuals ever passed (i.e. the plain solve would have converged)."""
     q_init = _c(q_init); pose12 = _c(pose12); n, nq = q_init.shape
-    q = np.empty((n, nq)); ok = np.empty(n, np.uint8); it = np.empty(n, np.int32)
+    q = np.empty((n, nq)); ok = np.empty(n, np.uint8); it = np.empty(n, np.int32); ever = np.empty(n, np.uint8)
     lib().orc_solve_success(ctypes.byref(table_c), ctypes.byref(scene_c), ctypes.c_int64(n), _p(q_init), _p(pose12),
-                            ctypes.c_double(eps), ctypes.c_double(dt), ctypes.c_int(max_iters), ctypes.c_int(threads),
-                            _p(q), _p(ok), _p(it))
+                            ctypes.c_double(eps), ctypes.c_double(dt), ctypes.c_int(max_iters), ctypes.c_double(damping),
+                            ctypes.c_int(threads), _p(q), _p(ok), _p(it), _p(ever))
+    if return_ever:
+        return q, ok.astype(bool), it, ever.astype(bool)
     return q, ok.astype(bool), it
 
 

@@ -200,11 +200,13 @@ def project_to_joint_limits(q):
 # The hot loop
 # --------------------------------------------------------------------------------------
 def computeqgrasppose(qcurrent, cube_R, cube_p, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS,
-                      collision=None, return_info=False):
+                      collision=None, return_info=False, damping=0.0):
     """inverse_geometry.computeqgrasppose (inverse_geometry.py:17-100), loop order preserved:
     residual check BEFORE the update, post-update q returned on exhaustion, `collision(q)`
     evaluated only when both norms pass (short-circuit at :70) and once more at :97.
-    `collision` is a callable q -> bool or None (treated as never colliding)."""
+    `collision` is a callable q -> bool or None (treated as never colliding).
+    `damping` = 0 is the reference (pinv, :83); > 0 replaces the step by the damped least-squares form
+    J^T (J J^T + damping I)^-1 e that BASELINE config 3 asks for on random restarts (not a reference setting)."""
     targets = hook_targets(np.asarray(cube_R, float), np.asarray(cube_p, float))
     q = np.array(qcurrent, dtype=np.float64).copy()
     success = False
@@ -220,7 +222,10 @@ def computeqgrasppose(qcurrent, cube_R, cube_p, *, eps=EPSILON, dt=DT, max_iters
             iters = it
             break
         J = np.vstack([frame_jacobian_local(q, 0, fk), frame_jacobian_local(q, 1, fk)])
-        vq = np.linalg.pinv(J) @ np.hstack([eL, eR])          # inverse_geometry.py:83
+        if damping > 0.0:
+            vq = J.T @ np.linalg.solve(J @ J.T + damping * np.eye(12), np.hstack([eL, eR]))
+        else:
+            vq = np.linalg.pinv(J) @ np.hstack([eL, eR])      # inverse_geometry.py:83
         q = q + vq * dt                                       # pin.integrate, all-revolute model (:86)
         q = project_to_joint_limits(q)                        # :89
     if collision is not None and collision(q):                # :97-98

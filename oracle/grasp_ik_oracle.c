@@ -157,8 +157,11 @@ static void hand_error(const se3_t* hand, const se3_t* target, double* e) {
 
 /* vq = pinv(J) e with numpy.linalg.pinv semantics (rcond = 1e-15 relative to the largest singular value;
  * inverse_geometry.py:83).  J is m x n row-major (m = 12, n = nq).  One-sided Jacobi SVD of W = J^T (n x m):
- * W = U S V^T  =>  pinv(J) = U S^+ V^T. */
-static void pinv_apply(const double* J, int m, int n, const double* e, double* vq) {
+ * W = U S V^T  =>  pinv(J) = U S^+ V^T.
+ * lambda > 0 (not a reference setting -- the reference is undamped; BASELINE config 3 asks for damping on random
+ * restarts): the damped least-squares step J^T (J J^T + lambda I)^-1 e = sum_j u_j s_j / (s_j^2 + lambda) (v_j . e),
+ * from the same SVD, no cutoff (every term is finite). */
+static void pinv_apply(const double* J, int m, int n, const double* e, double lambda, double* vq) {
   double W[ORC_MAX_NQ][12], V[12][12];
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < m; ++j) W[i][j] = J[j * n + i];
@@ -197,10 +200,10 @@ static void pinv_apply(const double* J, int m, int n, const double* e, double* v
   }
   for (int i = 0; i < n; ++i) vq[i] = 0.0;
   for (int j = 0; j < m; ++j) {
-    if (!(sig[j] > 1e-15 * smax)) continue;
+    if (lambda <= 0.0 && !(sig[j] > 1e-15 * smax)) continue;
     double ve = 0;
     for (int i = 0; i < m; ++i) ve += V[i][j] * e[i];
-    const double f = ve / (sig[j] * sig[j]); /* U[:,j] = W[:,j] / sig */
+    const double f = ve / (sig[j] * sig[j] + (lambda > 0.0 ? lambda : 0.0)); /* U[:,j] = W[:,j] / sig */
     for (int i = 0; i < n; ++i) vq[i] += W[i][j] * f;
   }
 }
@@ -220,7 +223,7 @@ static void hook_targets(const orc_table_t* t, const double* pose12, se3_t* tg) 
 /* inverse_geometry.computeqgrasppose (inverse_geometry.py:17-100) without the collision term; loop order kept:
  * residual test BEFORE the update, post-update q returned on exhaustion. */
 static int solve_one(const orc_table_t* t, const double* q0, const double* pose12, double eps, double dt,
-                     int max_iters, double* q, int* iters_out, double* resid_out) {
+                     int max_iters, double damping, double* q, int* iters_out, double* resid_out) {
   const int nq = t->nq;
   se3_t tg[2], oMi[ORC_MAX_NQ], hand[2];
   double e[12], J[12 * ORC_MAX_NQ], vq[ORC_MAX_NQ];
@@ -235,7 +238,7 @@ static int solve_one(const orc_table_t* t, const double* q0, const double* pose1
     nR = sqrt(e[6] * e[6] + e[7] * e[7] + e[8] * e[8] + e[9] * e[9] + e[10] * e[10] + e[11] * e[11]);
     if (nL < eps && nR < eps) { success = 1; break; }
     for (int h = 0; h < 2; ++h) frame_jacobian_local(t, oMi, &hand[h], h, J + 6 * nq * h);
-    pinv_apply(J, 12, nq, e, vq);
+    pinv_apply(J, 12, nq, e, damping, vq);
     for (int i = 0; i < nq; ++i) {
       double v = q[i] + vq[i] * dt;                 /* pin.integrate (:86) */
       v = v < t->lower[i] ? t->lower[i] : v;         /* projecttojointlimits (:89) */
@@ -283,7 +286,8 @@ int orc_jac(const orc_table_t* t, int64_t n, const double* q, double* jac /* [n]
 }
 
 int orc_solve(const orc_table_t* t, int64_t n, const double* q_init, const double* pose, double eps, double dt,
-              int max_iters, int threads, double* q_out, uint8_t* conv, int32_t* iters, double* resid /* [n][2] */) {
+              int max_iters, double damping, int threads, double* q_out, uint8_t* conv, int32_t* iters,
+              double* resid /* [n][2] */) {
   const int nq = t->nq;
 #ifdef _OPENMP
   omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
@@ -292,7 +296,7 @@ int orc_solve(const orc_table_t* t, int64_t n, const double* q_init, const doubl
   for (int64_t i = 0; i < n; ++i) {
     int it;
     double r[2];
-    conv[i] = (uint8_t)solve_one(t, q_init + i * nq, pose + i * 12, eps, dt, max_iters, q_out + i * nq, &it, r);
+    conv[i] = (uint8_t)solve_one(t, q_init + i * nq, pose + i * 12, eps, dt, max_iters, damping, q_out + i * nq, &it, r);
     if (iters) iters[i] = it;
     if (resid) { resid[2 * i] = r[0]; resid[2 * i + 1] = r[1]; }
   }
@@ -333,7 +337,7 @@ int orc_interpolate(int64_t n, const double* A, const double* B, const double* a
 /* path.project_path loop (path.py:137-160) for n edges: q_path [n][max_steps][nq]; returns n_valid per edge. */
 int orc_project_edges(const orc_table_t* t, int64_t n, int max_steps, const double* q_start, const double* pose_a,
                       const double* pose_b, const int32_t* num_steps, double eps, double dt, int max_iters,
-                      int threads, double* q_path, int32_t* n_valid, int32_t* iters_total) {
+                      double damping, int threads, double* q_path, int32_t* n_valid, int32_t* iters_total) {
   const int nq = t->nq;
 #ifdef _OPENMP
   omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
@@ -346,7 +350,7 @@ int orc_project_edges(const orc_table_t* t, int64_t n, int max_steps, const doub
     for (int step = 1; step <= num_steps[e] && step <= max_steps; ++step) {
       int it;
       se3_interpolate(pose_a + 12 * e, pose_b + 12 * e, (double)step / (double)num_steps[e], pose);
-      const int ok = solve_one(t, q, pose, eps, dt, max_iters, qn, &it, r);
+      const int ok = solve_one(t, q, pose, eps, dt, max_iters, damping, qn, &it, r);
       total += it;
       if (!ok) break;
       memcpy(q, qn, sizeof(double) * nq);

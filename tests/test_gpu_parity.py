@@ -420,6 +420,41 @@ def test_host_pipeline_equals_device_path(solver):
     assert torch.equal(q_h, q_d.cpu()) and torch.equal(ok_h, ok_d.cpu())
 
 
+def test_host_pipeline_unaligned_slabs_and_ownership(solver):
+    # (1) a multi-slab batch whose size is not a multiple of anything (100003 rows, 4 slabs) with POISONED staging
+    # buffers: a row read before its slab landed (or served from a stale cache line shared by two slabs) would be NaN.
+    # Interior slab boundaries are multiples of 32 rows and the kernel reads its inputs with ld.global.cg behind an
+    # acquire fence on the `ready` counter.  numpy (pageable) inputs go through the same path.
+    import gik_b200
+    from gik_b200.ops import _slab_bounds
+    n = 100003
+    b = _slab_bounds(n, 4)
+    assert b[0] == 0 and b[-1] == n and len(b) == 5 and all(x % 32 == 0 for x in b[1:-1])
+    P = make_poses(n, 83).astype(np.float32)
+    Q0 = np.random.default_rng(2).uniform(-0.1, 0.1, size=(n, 15)).astype(np.float32)
+    q_d, ok_d = gik_b200.computeqgrasppose_batch(solver, torch.from_numpy(Q0).cuda(), torch.from_numpy(P).cuda(), dtype=torch.float32)
+    solver._poison_staging = True
+    try:
+        for _ in range(3):
+            q_h, ok_h = gik_b200.computeqgrasppose_batch(solver, Q0, P, dtype=torch.float32)
+            assert torch.isfinite(q_h).all()
+            assert torch.equal(q_h, q_d.cpu()) and torch.equal(ok_h, ok_d.cpu())
+    finally:
+        solver._poison_staging = False
+    # (2) ownership: results of successive calls do not alias (fresh tensors by default)
+    Pa = torch.from_numpy(make_poses(3000, 84)).float(); Pb = torch.from_numpy(make_poses(3000, 85)).float()
+    qa, oka = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), Pa)
+    qa_copy = qa.clone()
+    qb, okb = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), Pb)
+    assert qa.data_ptr() != qb.data_ptr() and torch.equal(qa, qa_copy) and not torch.equal(qa, qb)
+    # (3) out=: the allocation-free path stores into the caller's pinned buffers
+    qo = torch.empty((3000, 15)).pin_memory(); co = torch.empty(3000, dtype=torch.uint8).pin_memory()
+    q2, ok2 = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), Pb, out=(qo, co))
+    assert q2.data_ptr() == qo.data_ptr() and torch.equal(q2, qb) and torch.equal(ok2, okb)
+    with pytest.raises(ValueError):
+        gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), Pb, out=(torch.empty((3000, 15)), co))   # not pinned
+
+
 def test_other_robot_tables_generic_instantiation(table, c_oracle):
     # a table of the same topology but other dimensions (no zero translation components, other hand / hook frames,
     # narrower limits) runs the GENERIC kernel instantiations (TZ = 0), not the Nextage-specialised ones

@@ -84,3 +84,19 @@ def test_hostsim_random_tables_of_the_supported_topology(table, hostsim, c_oracl
         both = ok & oko
         if both.any():
             assert np.quantile(np.abs(q[both] - qo[both]).max(axis=1), 0.9) < 1e-9 and (it[both] == ito[both]).mean() > 0.9
+
+
+def test_hostsim_damped_restarts_match_oracle(table, table_c, hostsim, c_oracle):
+    # config 3's setting: damping 1e-6, initial q uniform in [lower, upper] over all 15 joints (restart 0 = zeros)
+    rng = np.random.default_rng(13)
+    n = 64
+    P = np.repeat(make_poses(8, 14), 8, axis=0)
+    Q0 = rng.uniform(table.lower, table.upper, size=(n, 15)); Q0[::8] = 0.0
+    qo, oko, ito, ro = c_oracle.solve(table_c, Q0, P, damping=1e-6)
+    q, ok, it, r = hostsim.solve(table_c, Q0, P, np.float64, damping=1e-6)
+    assert (ok == oko).mean() >= 0.95
+    both = ok & oko
+    assert both.sum() >= 8
+    d = np.abs(q[both] - qo[both]).max(axis=1)
+    assert np.quantile(d, 0.9) < 1e-8 and (it[both] == ito[both]).mean() >= 0.9
+    assert np.abs(r[both] - ro[both]).max() < 1e-9

@@ -138,3 +138,30 @@ def test_failed_problems_can_be_chaotic_between_the_two_restatements(table_c, c_
     fail = [k for k in range(len(idx)) if not okc[k] and not okn[k]]
     assert len(conv) >= 2 and max(d[k] for k in conv) < 1e-12
     assert fail and max(d[k] for k in fail) > 1e-3
+
+
+def test_damped_step_oracles_agree(table, table_c, c_oracle):
+    """BASELINE config 3's solver setting (damping 1e-6, starts uniform inside the joint limits) in BOTH restatements:
+    the numpy one solves (J J^T + lambda I) z = e directly, the C one goes through its SVD.  lambda = 0 stays the
+    reference's pinv."""
+    rng = np.random.default_rng(8)
+    n = 10
+    P = make_poses(n, 12)
+    Q0 = rng.uniform(table.lower, table.upper, size=(n, 15)); Q0[0] = 0.0
+    for lam in (1e-6, 1e-2):
+        # 25 iterations: every trajectory still agrees to round-off (random starts brush singular poses and joint limits,
+        # where two SVD/solve routes drift apart over hundreds of iterations -- DESIGN.md "Sensitivity")
+        q25 = c_oracle.solve(table_c, Q0, P, damping=lam, max_iters=25)[0]
+        q, ok, it, res = c_oracle.solve(table_c, Q0, P, damping=lam, max_iters=400)
+        for i in range(n):
+            qn = o.computeqgrasppose(Q0[i], np.eye(3), P[i, 9:], damping=lam, max_iters=25)[0]
+            assert np.abs(qn - q25[i]).max() < 1e-9
+            qn, okn, itn, rn = o.computeqgrasppose(Q0[i], np.eye(3), P[i, 9:], damping=lam, max_iters=400, return_info=True)
+            assert okn == ok[i]
+            if okn:
+                assert itn == it[i] and np.abs(qn - q[i]).max() < 1e-8
+    # one damped step is shorter than the undamped one, and lambda -> 0 recovers it
+    q_u = c_oracle.solve(table_c, np.zeros((n, 15)), P, max_iters=1)[0]
+    q_d = c_oracle.solve(table_c, np.zeros((n, 15)), P, max_iters=1, damping=1.0)[0]
+    q_e = c_oracle.solve(table_c, np.zeros((n, 15)), P, max_iters=1, damping=1e-14)[0]
+    assert (np.abs(q_d).sum(1) < np.abs(q_u).sum(1)).all() and np.abs(q_e - q_u).max() < 1e-9
