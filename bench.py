@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--early-stop", action="store_true",
                     help="fast preset GIK_F_EARLY_STOP (NOT the reference's semantics for failed problems; never the default)")
     ap.add_argument("--kernel", default=None, choices=["lane", "pair", "lane1"], help="force a thread mapping (default: launcher's choice)")
+    ap.add_argument("--step", default="auto", choices=["auto", "cholesky"],
+                    help="form of the undamped step: auto = spherical-wrist 3x3 solves where the table allows it (default), "
+                         "cholesky = always the general 6x6 block-Cholesky form (A/B)")
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = "f64" if args.config == 3 else "f32"
@@ -340,6 +343,7 @@ def run_b200(args):
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     esz = 4 if args.dtype == "f32" else 8
     solver = gik_b200.GraspIK(gik_b200.nextage_table(), dev)
+    solver.force_cholesky = args.step == "cholesky"
 
     scaling = "weak"
     if args.config == 2:

@@ -87,6 +87,12 @@ typedef struct gik_params_s {
  * unchanged; success flags agree on 99.9997 % (fp32) / 99.993 % (fp64) of 2^20 workspace problems -- the exceptions
  * are late convergers (850-1000 iterations) that are given up on; there are no false successes. */
 #define GIK_F_EARLY_STOP 16
+/* Form of the step.  By default an UNDAMPED step (damping = 0) on a table with a spherical wrist (the Nextage arms: the
+ * axes of the last three joints of each arm meet in one point) is computed as dq_arm = u - kappa w with u = A^-1 e,
+ * w = A^-1 c through two 3x3 solves per hand at the wrist centre -- algebraically the same pinv(J) e as the reference's
+ * (inverse_geometry.py:83) wherever J has full row rank.  This flag keeps the general form (6x6 block Cholesky of
+ * A A^T + lambda I and Sherman-Morrison), which damping > 0 and other tables always use.  For A/B runs and tests. */
+#define GIK_F_CHOLESKY 32
 
 typedef struct gik_handle_s* gik_handle_t;
 

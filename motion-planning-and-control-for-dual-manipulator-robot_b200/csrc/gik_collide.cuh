@@ -200,13 +200,38 @@ GIK_HD Shape<T> make_shape(const DevGeom<T>& g, const T* M) {
   return S;
 }
 
+// The shape ERODED by `shrink` (the points whose shrink-ball lies inside it): box -> smaller box, sphere -> smaller
+// sphere, cylinder -> thinner and shorter cylinder.  Returns false when nothing is left.
+template <typename T>
+GIK_HD bool erode_shape(Shape<T>& S, T shrink) {
+  S.s0 -= shrink;
+  if (S.type != GEOM_SPHERE) S.s1 -= shrink;
+  if (S.type == GEOM_BOX) S.s2 -= shrink;
+  return S.s0 > T(0) && (S.type == GEOM_SPHERE || S.s1 > T(0)) && (S.type != GEOM_BOX || S.s2 > T(0));
+}
+
+// Narrow phase of one pair.  margin >= 0: does (A inflated by margin) intersect B  (collision: 0; clearance: the
+// threshold).  margin < 0: do A and B, each ERODED by |margin| / 2, intersect -- a PERSISTENT collision: the two solids
+// keep intersecting under any relative displacement of their points smaller than |margin| (used to settle the
+// reference's keep-descending-while-colliding tail without testing every iterate, gik_collide_impl.cuh).
+template <typename T>
+GIK_HD bool narrow_hits(const DevGeom<T>& ga, const T* Ma, const DevGeom<T>& gb, const T* Mb, T margin) {
+  Shape<T> A = make_shape(ga, Ma), B = make_shape(gb, Mb);
+  if (margin < T(0)) {
+    const T sh = T(-0.5) * margin;
+    if (!erode_shape(A, sh) || !erode_shape(B, sh)) return false;
+    return gjk_intersect(A, B, T(0));
+  }
+  return gjk_intersect(A, B, margin);
+}
+
 // pair (a, b) with world placements Ma, Mb: bounding spheres, then GJK
 template <typename T>
 GIK_HD bool pair_hits(const DevGeom<T>& ga, const T* Ma, const DevGeom<T>& gb, const T* Mb, T margin) {
   const T dx = Ma[9] - Mb[9], dy = Ma[10] - Mb[10], dz = Ma[11] - Mb[11];
-  const T reach = ga.bound + gb.bound + margin;
+  const T reach = ga.bound + gb.bound + max_(margin, T(0));
   if (dx * dx + dy * dy + dz * dz > reach * reach) return false;
-  return gjk_intersect(make_shape(ga, Ma), make_shape(gb, Mb), margin);
+  return narrow_hits(ga, Ma, gb, Mb, margin);
 }
 
 }  // namespace gik

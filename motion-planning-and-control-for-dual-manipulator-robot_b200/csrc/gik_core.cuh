@@ -49,6 +49,7 @@ struct ArmConst {
   T g6[21];     // lower triangle (i >= j at i(i+1)/2 + j) of tip_col tip_col^T: the tip joint's constant share of G = A A^T
   T hook_R[9];  // hook frame on the cube
   T hook_p[3];
+  T rw[3];      // wrist centre (common point of the axes of chain joints 4, 5, 6) in the hand frame; spherical-wrist tables only
 };
 
 template <typename T>
@@ -67,6 +68,11 @@ struct DevTable {
 // (0,y,z) | (x,0,z) | (x,0,0) | (0,0,z).  Kernels are instantiated for "no zeros known" (TZ = 0, any table of the
 // compiled topology) and for this pattern; the launcher picks the specialisation when the table has at least these zeros.
 constexpr uint32_t kNextageTZ = (3u << 0) | (3u << 6) | (1u << 9) | (1u << 13) | (6u << 15) | (3u << 18);
+// Spherical wrist: joint 5's origin lies on joint 4's axis (t[5] = (x, 0, 0), joint 4 turns about x) and on joint 6's
+// axis (t[6] = (0, 0, z), joint 6 turns about z), so the axes of chain joints 4, 5, 6 meet in one point.  Part of the
+// Nextage pattern; the undamped step then decouples into two 3x3 solves per hand (hand_wrist_phase1).
+constexpr uint32_t kWristTZ = (6u << 15) | (3u << 18);
+static_assert((kNextageTZ & kWristTZ) == kWristTZ, "the Nextage pattern includes the spherical wrist");
 
 // ------------------------------------------------------------------------------------------------------
 // scalar helpers
@@ -76,11 +82,13 @@ template <> struct Num<float> {
   static constexpr float kPivotFloor = 1e-30f;  // Cholesky pivot guard (singular arm Jacobian)
   static constexpr float kSeriesT2 = 0.25f;     // theta^2 below which log6's alpha/beta use their series
   static constexpr float kTinyS = 1e-18f;
+  static constexpr float kRcpCap = 1e12f;       // |1 / det| cap of the 3x3 solves (singular arm / wrist)
 };
 template <> struct Num<double> {
   static constexpr double kPivotFloor = 1e-280;
   static constexpr double kSeriesT2 = 1e-4;
   static constexpr double kTinyS = 1e-150;
+  static constexpr double kRcpCap = 1e100;
 };
 
 // fp32 device versions are single MUFU instructions (rsqrt/sqrt/rcp .approx.ftz, <= 2 ulp): the IEEE library
@@ -274,7 +282,8 @@ GIK_HD F2& operator-=(F2& a, F2 b) { a = a - b; return a; }
 GIK_HD F2 max_(F2 a, F2 b) { return F2(max_(a.x, b.x), max_(a.y, b.y)); }
 GIK_HD F2 min_(F2 a, F2 b) { return F2(min_(a.x, b.x), min_(a.y, b.y)); }
 GIK_HD F2 rsqrt_(F2 a) { return F2(rsqrt_(a.x), rsqrt_(a.y)); }
-template <> struct Num<F2> { static constexpr float kPivotFloor = 1e-30f; };
+GIK_HD F2 rcp_(F2 a) { return F2(rcp_(a.x), rcp_(a.y)); }
+template <> struct Num<F2> { static constexpr float kPivotFloor = 1e-30f; static constexpr float kRcpCap = 1e12f; };
 
 // FAST = MUFU-based sin/cos (abs error ~5e-7 on [-pi, pi]); accurate otherwise.
 template <bool FAST>
@@ -626,20 +635,173 @@ GIK_HD void hand_phase2(const HandState<T>& hs, T kappa, T (&dq)[6]) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Spherical-wrist form of the UNDAMPED step (lambda = 0; tables with kWristTZ).
+//
+// With J = [c_L A_L 0; c_R 0 A_R] of full row rank, pinv(J) e = J^T (J J^T)^-1 e, and because the arm blocks A are
+// SQUARE, A^T (A A^T)^-1 = A^-1: with u = A^-1 e, w = A^-1 c (per hand)
+//     dq_chest = kappa = (u_L.w_L + u_R.w_R) / (1 + |w_L|^2 + |w_R|^2),      dq_arm = u - kappa w
+// (Sherman-Morrison on blockdiag(A A^T) + c c^T, the same identity as the Cholesky path, with G^-1 = A^-T A^-1).  No Gram
+// matrix, no factorisation of A A^T, no A^T product, and the conditioning is cond(A) instead of cond(A)^2.
+// The min-norm solution is unchanged when both sides are multiplied by an invertible X (J -> X J, e -> X e), so every
+// hand's rows may be expressed at ANOTHER REFERENCE POINT: v' = v + w x r moves the point where the linear velocity
+// is taken from the hand origin to r.  At the WRIST CENTRE (the common point of the axes of chain joints 4, 5, 6) the
+// linear parts of those three columns vanish, A' = [M 0; Wa Wb] is block triangular, and A'^-1 is two 3x3 solves:
+//     M x_123 = rhs_v                      M = [m1 m2 m3], m_K = (b_K - r) x a_K           (Cramer, one reciprocal)
+//     Wb x_456 = rhs_w - Wa x_123          Wb = [a4 a5 a6] with a5 _|_ a4, a5 _|_ a6, |a_K| = 1 (consecutive
+//                                          perpendicular axes):  x5 = a5.rho, x4 = (n.rho)/(n.a4) with n = a5 x a6,
+//                                          x6 = a6.rho - (a6.a4) x4                                  (one reciprocal)
+// The chain is walked as before (backwards from the hand frame) with the translation taken relative to the wrist
+// centre: it is exactly 0 at joint 5, so only joints 0..3 need their linear parts.  Reciprocals are capped
+// (Num<T>::kRcpCap) where the arm or the wrist is singular, as the Cholesky path floors its pivots.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+struct WristState { T u[6], w[6]; };
+
+template <typename T, int K, int OFF>
+GIK_HD void chain_rotate(const T (&cs)[kActive], const T (&sn)[kActive], T (&B)[9]) {   // B <- B * Rot(axis_K, -q_K)
+  constexpr int AX = chain_axis(K), I = (AX + 1) % 3, J = (AX + 2) % 3;
+  constexpr int SLOT = K == 0 ? 0 : OFF + K;
+  const T c = cs[SLOT], s = sn[SLOT];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const T bi = B[3 * r + I], bj = B[3 * r + J];
+    B[3 * r + I] = c * bi - s * bj;
+    B[3 * r + J] = s * bi + c * bj;
+  }
+}
+template <typename T, int K, uint32_t TZ>
+GIK_HD void chain_translate(const ArmConst<T>& ac, const T (&B)[9], T (&b)[3]) {       // b <- b - B * t_K
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    if constexpr (!((TZ >> (3 * K + 0)) & 1u)) b[r] -= B[3 * r] * ac.t[K][0];
+    if constexpr (!((TZ >> (3 * K + 1)) & 1u)) b[r] -= B[3 * r + 1] * ac.t[K][1];
+    if constexpr (!((TZ >> (3 * K + 2)) & 1u)) b[r] -= B[3 * r + 2] * ac.t[K][2];
+  }
+}
+template <typename T>
+GIK_HD void cross3(const T (&a)[3], const T (&b)[3], T (&o)[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <typename T>
+GIK_HD T dot3(const T (&a)[3], const T (&b)[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T>
+GIK_HD T rcp_capped(T d) { return min_(max_(rcp_(d), T(-Num<T>::kRcpCap)), T(Num<T>::kRcpCap)); }
+
+template <typename T, int OFF, uint32_t TZ>
+GIK_HD void hand_wrist_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], const T (&sn)[kActive], const T (&tgt)[12],
+                              WristState<T>& ws, T& Sy, T& Sz, T& resid2) {
+  static_assert((TZ & kWristTZ) == kWristTZ, "spherical-wrist path instantiated for a table pattern without one");
+  static_assert(chain_axis(4) == 0 && chain_axis(5) == 1 && chain_axis(6) == 2 && chain_axis(2) == 1 && chain_axis(3) == 1 &&
+                chain_axis(1) == 2 && chain_axis(0) == 2, "axis pattern assumed below");
+  T B[9], b[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
+  // joint 6 (z): its axis is constant in the hand frame; after its step the translation relative to the wrist centre is 0
+  const T a6[3] = {B[2], B[5], B[8]};
+  chain_rotate<T, 6, OFF>(cs, sn, B);
+  // joint 5 (y)
+  const T a5[3] = {B[1], B[4], B[7]};
+  chain_rotate<T, 5, OFF>(cs, sn, B);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) b[r] = -(B[3 * r] * ac.t[5][0]);
+  // joint 4 (x): still on the wrist centre's axes -- no linear part
+  const T a4[3] = {B[0], B[3], B[6]};
+  chain_rotate<T, 4, OFF>(cs, sn, B);
+  chain_translate<T, 4, TZ>(ac, B, b);
+  // joints 3, 2 (y, y: parallel axes, the rotation about y leaves column 1 alone), 1 (z), chest (z: the same axis as joint 1)
+  const T ay[3] = {B[1], B[4], B[7]};
+  T m3[3], m2[3], m1[3], m0[3];
+  cross3(b, ay, m3);
+  chain_rotate<T, 3, OFF>(cs, sn, B);
+  chain_translate<T, 3, TZ>(ac, B, b);
+  cross3(b, ay, m2);
+  chain_rotate<T, 2, OFF>(cs, sn, B);
+  chain_translate<T, 2, TZ>(ac, B, b);
+  const T az[3] = {B[2], B[5], B[8]};
+  cross3(b, az, m1);
+  chain_rotate<T, 1, OFF>(cs, sn, B);
+  chain_translate<T, 1, TZ>(ac, B, b);
+  cross3(b, az, m0);
+  chain_rotate<T, 0, OFF>(cs, sn, B);
+  chain_translate<T, 0, TZ>(ac, B, b);
+  // (B, b + rw) = hand^-1: the error in the hand frame, then moved to the wrist centre
+  T bf[3], e[6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) bf[r] = b[r] + ac.rw[r];
+  ErrMid<T> em;
+  hand_error_pre(B, bf, tgt, em);
+  hand_error_post(em, e);
+  resid2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3] + e[4] * e[4] + e[5] * e[5];
+  const T ew[3] = {e[3], e[4], e[5]};
+  T ev[3];
+  cross3(ew, ac.rw, ev);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) ev[r] += e[r];
+  // M x_123 = rhs_v for rhs = e' and the chest column c' = [m0; az]
+  T c1[3], c2[3], c3[3];
+  cross3(m2, m3, c1);
+  cross3(m3, m1, c2);
+  cross3(m1, m2, c3);
+  const T rdet = rcp_capped(dot3(m1, c1));
+  T (&u)[6] = ws.u;
+  T (&w)[6] = ws.w;
+  u[0] = dot3(c1, ev) * rdet; u[1] = dot3(c2, ev) * rdet; u[2] = dot3(c3, ev) * rdet;
+  w[0] = dot3(c1, m0) * rdet; w[1] = dot3(c2, m0) * rdet; w[2] = dot3(c3, m0) * rdet;
+  // rho = rhs_w - a1 x1 - ay (x2 + x3)
+  T ru[3], rc[3];
+  const T su = u[1] + u[2], sw = w[1] + w[2], w0m = T(1) - w[0];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    ru[r] = ew[r] - az[r] * u[0] - ay[r] * su;
+    rc[r] = az[r] * w0m - ay[r] * sw;
+  }
+  // wrist: [a4 a5 a6] x_456 = rho
+  T n[3];
+  cross3(a5, a6, n);
+  const T rd = rcp_capped(dot3(n, a4)), g = dot3(a6, a4);
+  u[3] = dot3(n, ru) * rd; u[4] = dot3(a5, ru); u[5] = dot3(a6, ru) - g * u[3];
+  w[3] = dot3(n, rc) * rd; w[4] = dot3(a5, rc); w[5] = dot3(a6, rc) - g * w[3];
+  Sy = u[0] * w[0]; Sz = w[0] * w[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) { Sy += u[i] * w[i]; Sz += w[i] * w[i]; }
+}
+
+template <typename T>
+GIK_HD void hand_wrist_phase2(const WristState<T>& ws, T kappa, T (&dq)[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dq[k] = ws.u[k] - kappa * ws.w[k];
+}
+
 // Sherman-Morrison coupling of the two arm blocks through the shared chest joint: dq_chest = c.D^-1 e / (1 + c.D^-1 c)
 template <typename T>
 GIK_HD T chest_rate(T SyL, T SzL, T SyR, T SzR) { return div_(SyL + SyR, T(1) + (SzL + SzR)); }
 
 // One full iteration at q: SQUARED residual norms of both hands and the step direction dq = J^+ e.  (The predicate
 // ||e|| < eps of inverse_geometry.py:70 is evaluated as ||e||^2 < eps^2; the norm itself is only taken when a result is stored.)
-template <typename T, bool FAST, uint32_t TZ = 0>
+template <typename T, bool FAST, uint32_t TZ = 0, bool WRIST = false>
 GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T (&tgt)[2][12], T lambda,
                          T (&dq)[kActive], T& resid2L, T& resid2R) {
   T cs[kActive], sn[kActive];
 #pragma unroll
   for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
-  HandState<T> hL, hR;
   T SyL, SzL, SyR, SzR;
+  if constexpr (WRIST) {          // lambda = 0 on a spherical-wrist table: two 3x3 solves per hand
+    WristState<T> wL, wR;
+    hand_wrist_phase1<T, 0, TZ>(tab.arm[0], cs, sn, tgt[0], wL, SyL, SzL, resid2L);
+    hand_wrist_phase1<T, 6, TZ>(tab.arm[1], cs, sn, tgt[1], wR, SyR, SzR, resid2R);
+    const T kappa = chest_rate(SyL, SzL, SyR, SzR);
+    dq[0] = kappa;
+    T dL[6], dR[6];
+    hand_wrist_phase2(wL, kappa, dL);
+    hand_wrist_phase2(wR, kappa, dR);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { dq[1 + k] = dL[k]; dq[7 + k] = dR[k]; }
+    return;
+  }
+  HandState<T> hL, hR;
   // the fp64 lane kernel keeps the tip products so that it stays bit-identical to the fp64 pair kernel (the default)
   constexpr bool G6 = sizeof(T) == 4;
   hand_phase1<T, 0, TZ, G6>(tab.arm[0], cs, sn, tgt[0], lambda, hL, SyL, SzL, resid2L);
@@ -662,7 +824,7 @@ struct PackedTable {
   float lo0, hi0;          // chest limits
 };
 
-template <uint32_t TZ>
+template <uint32_t TZ, bool WRIST = false>
 GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[6], const F2 (&tgt2)[12], float lambda,
                                 float& dq0, F2 (&dq2)[6], float& resid2L, float& resid2R) {
   F2 cs[kActive], sn[kActive];      // only chain slots 0..6 are used
@@ -678,12 +840,20 @@ GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[
     sincos_<true>(q2[k].y, sr, cr);
     cs[1 + k] = F2(cl, cr); sn[1 + k] = F2(sl, sr);
   }
-  HandState<F2> hs;
   F2 Sy, Sz, r2;
-  hand_phase1<F2, 0, TZ, true>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
-  const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
-  dq0 = kappa;
-  hand_phase2(hs, F2(kappa), dq2);
+  if constexpr (WRIST) {
+    WristState<F2> ws;
+    hand_wrist_phase1<F2, 0, TZ>(pt.arm, cs, sn, tgt2, ws, Sy, Sz, r2);
+    const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
+    dq0 = kappa;
+    hand_wrist_phase2(ws, F2(kappa), dq2);
+  } else {
+    HandState<F2> hs;
+    hand_phase1<F2, 0, TZ, true>(pt.arm, cs, sn, tgt2, F2(lambda), hs, Sy, Sz, r2);
+    const float kappa = chest_rate(Sy.x, Sz.x, Sy.y, Sz.y);
+    dq0 = kappa;
+    hand_phase2(hs, F2(kappa), dq2);
+  }
   resid2L = r2.x; resid2R = r2.y;
 }
 

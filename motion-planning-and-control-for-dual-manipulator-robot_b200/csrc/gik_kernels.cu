@@ -91,7 +91,7 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
   }
 }
 
-template <typename T, int MODE, uint32_t TZ>
+template <typename T, int MODE, uint32_t TZ, bool WRIST = false>
 __global__ void __launch_bounds__(GIK_THREADS, Launch<T>::kMinBlocks)
 gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
   const int lane = threadIdx.x & 31;
@@ -165,7 +165,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
 
     // ---------------- one descent iteration for every lane ----------------
     T dq[kActive], rL, rR;
-    ik_iteration<T, true, TZ>(tab, q, tgt, a.lambda, dq, rL, rR);
+    ik_iteration<T, true, TZ, WRIST>(tab, q, tgt, a.lambda, dq, rL, rR);
     const bool ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
     bool stalled = false;
     if (a.early_stop && (it & 63) == 63) {
@@ -245,8 +245,11 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
 #ifndef GIK_LANE2_INNER
 #define GIK_LANE2_INNER true   // measured against the single-loop form on 2^20 problems: 38.30 -> 36.75 ms (27.3 -> 28.5 M solves/s)
 #endif
-template <int MODE, uint32_t TZ>
-__global__ void __launch_bounds__(GIK_THREADS, GIK_MINB_LANE2)
+#ifndef GIK_MINB_LANE2_WRIST
+#define GIK_MINB_LANE2_WRIST 3   // 168 registers, no spills: 39.9 M solves/s on 2^20 problems against 39.5 M at 4 blocks (128 registers, ~270 B of spills), 34.0 M at 5, 23.6 M at 6
+#endif
+template <int MODE, uint32_t TZ, bool WRIST = false>
+__global__ void __launch_bounds__(GIK_THREADS, (WRIST ? GIK_MINB_LANE2_WRIST : GIK_MINB_LANE2))
 gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid_constant__ PackedTable pt,
                        const __grid_constant__ SolveArgs<float> a) {
   using T = float;
@@ -349,7 +352,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
     for (;;) {
       T dq0;
       F2 dq2[6];
-      ik_iteration_packed<TZ>(pt, q0, q2, tgt2, a.lambda, dq0, dq2, rL, rR);
+      ik_iteration_packed<TZ, WRIST>(pt, q0, q2, tgt2, a.lambda, dq0, dq2, rL, rR);
       ok = (rL < a.eps2) && (rR < a.eps2) && (it < a.max_iters);
       bool stalled = false;
       if (a.early_stop && (it & 63) == 63) {
@@ -453,10 +456,14 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
 #ifndef GIK_MINB_PAIR_F64_HOIST
 #define GIK_MINB_PAIR_F64_HOIST 1   // launches of <= GIK_F64_HOIST_WARPS warps per SM only: registers are free (252 used, two blocks per SM)
 #endif
-template <typename T, bool HOIST> struct LaunchPair;
-template <bool HOIST> struct LaunchPair<float, HOIST>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
-template <> struct LaunchPair<double, false> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64; };
-template <> struct LaunchPair<double, true>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64_HOIST; };
+#ifndef GIK_MINB_PAIR_F64_WRIST
+#define GIK_MINB_PAIR_F64_WRIST 4   // large-batch fp64 instantiation of the spherical-wrist step
+#endif
+template <typename T, bool HOIST, bool WRIST> struct LaunchPair;
+template <bool HOIST, bool WRIST> struct LaunchPair<float, HOIST, WRIST>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F32; };
+template <> struct LaunchPair<double, false, false> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64; };
+template <> struct LaunchPair<double, false, true> { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64_WRIST; };
+template <bool WRIST> struct LaunchPair<double, true, WRIST>  { static constexpr int kMinBlocks = GIK_MINB_PAIR_F64_HOIST; };
 
 // HOIST: the hand's constants are selected into registers once instead of being fetched by lane-indexed constant loads
 // (39 LDC + their scoreboard waits per iteration), and the tip joint's constant outer product then comes from the table
@@ -464,8 +471,8 @@ template <> struct LaunchPair<double, true>  { static constexpr int kMinBlocks =
 // single solves -- where the time is the LATENCY of one chain and registers are free).  fp64: only for launches that fit
 // its two resident blocks per SM (<= 8 warps per SM); the large-batch fp64 kernel is bound by the FP64 pipe at 168 registers and keeps
 // the constant loads.
-template <typename T, int MODE, uint32_t TZ, bool HOIST = (sizeof(T) == 4)>
-__global__ void __launch_bounds__(GIK_THREADS, (LaunchPair<T, HOIST>::kMinBlocks))
+template <typename T, int MODE, uint32_t TZ, bool HOIST = (sizeof(T) == 4), bool WRIST = false>
+__global__ void __launch_bounds__(GIK_THREADS, (LaunchPair<T, HOIST, WRIST>::kMinBlocks))
 gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
   const int lane = threadIdx.x & 31;
   const int h = lane & 1;                       // hand of this lane
@@ -484,7 +491,10 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
 #pragma unroll
     for (int i = 0; i < 9; ++i) acr.finv_R[i] = h ? R.finv_R[i] : L.finv_R[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { acr.finv_p[i] = h ? R.finv_p[i] : L.finv_p[i]; acr.tip_lin[i] = h ? R.tip_lin[i] : L.tip_lin[i]; }
+    for (int i = 0; i < 3; ++i) {
+      acr.finv_p[i] = h ? R.finv_p[i] : L.finv_p[i]; acr.tip_lin[i] = h ? R.tip_lin[i] : L.tip_lin[i];
+      acr.rw[i] = h ? R.rw[i] : L.rw[i];
+    }
 #pragma unroll
     for (int i = 0; i < 21; ++i) acr.g6[i] = h ? R.g6[i] : L.g6[i];      // read by the fp32 instantiation only
     lim_lo[0] = tab.lo[0]; lim_hi[0] = tab.hi[0];
@@ -578,14 +588,17 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     for (;;) {
       T cs[kActive], sn[kActive], Sy, Sz, dqa[6];
       HandState<T> hs;
+      WristState<T> wst;
 #pragma unroll
       for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
       // (fp64 keeps the tip products in the Gram matrix: bit-identical to the fp64 lane kernel)
-      hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, lambda, hs, Sy, Sz, r);
+      if constexpr (WRIST) hand_wrist_phase1<T, 0, TZ>(acl, cs, sn, tgt, wst, Sy, Sz, r);
+      else hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, lambda, hs, Sy, Sz, r);
       const T Sy_o = __shfl_xor_sync(0xffffffffu, Sy, 1), Sz_o = __shfl_xor_sync(0xffffffffu, Sz, 1);
       const T r_o = __shfl_xor_sync(0xffffffffu, r, 1);
       const T kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
-      hand_phase2(hs, kappa, dqa);
+      if constexpr (WRIST) hand_wrist_phase2(wst, kappa, dqa);
+      else hand_phase2(hs, kappa, dqa);
       const T rL = h ? r_o : r, rR = h ? r : r_o;
       ok = (rL < eps2) && (rR < eps2) && (it < max_iters);
       bool stalled = false;
@@ -791,7 +804,7 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
   if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
-      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP)) != 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP | GIK_F_CHOLESKY)) != 0 ||
       (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
@@ -837,13 +850,27 @@ int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* b
 // below that.  fp64: always the pair kernel -- one hand per lane halves the live state, which at 2 registers per value
 // is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
 // params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
+// Which form of the step a launch runs: the spherical-wrist form (two 3x3 solves per hand) needs an undamped step and
+// a table with the wrist's zero pattern (instantiated for the Nextage pattern); everything else -- damping > 0, other
+// tables of the compiled topology, GIK_F_CHOLESKY -- takes the block Cholesky + Sherman-Morrison form.
+template <typename T>
+bool use_wrist(gik_handle_t h, const gik_params_t* prm) {
+  const DevTable<T>& tab = table_of<T>(h);
+  return (tab.tzero & kNextageTZ) == kNextageTZ && prm->damping == 0.0 && !(prm->flags & GIK_F_CHOLESKY);
+}
+
+// fp32: lane kernel when the batch can give (at least) half of the lanes of every resident warp a problem, pair kernel
+// below that.  fp64: always the pair kernel -- one hand per lane halves the live state, which at 2 registers per value
+// is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
+// params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
 template <typename T, int MODE>
-int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_warp, bool* pair, bool* hoist = nullptr) {
+int choose_launch(gik_handle_t h, int64_t n, int flags, bool wrist, int* blocks, int* per_warp, bool* pair, bool* hoist = nullptr) {
   int64_t max_warps = 0;
   int rc;
   if constexpr (sizeof(T) == 4) {
-    rc = (flags & GIK_F_SCALAR_LANE) ? grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps)
-                                     : grid_dims(h, gik_solve_lane2_kernel<MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+    if (flags & GIK_F_SCALAR_LANE) rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+    else if (wrist) rc = grid_dims(h, gik_solve_lane2_kernel<MODE, kNextageTZ, true>, n, 32, blocks, per_warp, &max_warps);
+    else rc = grid_dims(h, gik_solve_lane2_kernel<MODE, 0>, n, 32, blocks, per_warp, &max_warps);
   } else {
     rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
   }
@@ -856,10 +883,13 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, int* blocks, int* per_wa
   if (hoist) *hoist = hz;
   if (*pair) {
     if constexpr (sizeof(T) == 8) {
-      rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, true>, n, 16, blocks, per_warp, nullptr)
-              : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, false>, n, 16, blocks, per_warp, nullptr);
+      if (wrist) rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr)
+                         : grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, false, true>, n, 16, blocks, per_warp, nullptr);
+      else rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, true>, n, 16, blocks, per_warp, nullptr)
+                   : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, false>, n, 16, blocks, per_warp, nullptr);
     } else {
-      rc = grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
+      rc = wrist ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr)
+                 : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
     }
   }
   return rc;
@@ -876,7 +906,8 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   if (g.err != cudaSuccess) return (int)g.err;
   int blocks = 0, lanes = 32;
   bool pair = false, hoist = false;
-  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, &blocks, &lanes, &pair, &hoist);
+  const bool wrist = use_wrist<T>(h, prm);
+  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, wrist, &blocks, &lanes, &pair, &hoist);
   if (rc) return rc;
   a.lanes = lanes;
   a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
@@ -885,29 +916,36 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   const DevTable<T>& tab = table_of<T>(h);
   const bool nx = (tab.tzero & kNextageTZ) == kNextageTZ;   // table has (at least) the Nextage zero pattern: skip those FMAs
   cudaStream_t st = (cudaStream_t)stream;
+  constexpr uint32_t NX = kNextageTZ;
   if (pair) {
     if constexpr (sizeof(T) == 8) {
       if (hoist) {
-        if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        if (wrist) gik_solve_pair_kernel<T, MODE, NX, true, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        else if (nx) gik_solve_pair_kernel<T, MODE, NX, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
         else gik_solve_pair_kernel<T, MODE, 0, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
       } else {
-        if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ, false><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        if (wrist) gik_solve_pair_kernel<T, MODE, NX, false, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+        else if (nx) gik_solve_pair_kernel<T, MODE, NX, false><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
         else gik_solve_pair_kernel<T, MODE, 0, false><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
       }
     } else {
-      if (nx) gik_solve_pair_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      if (wrist) gik_solve_pair_kernel<T, MODE, NX, true, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      else if (nx) gik_solve_pair_kernel<T, MODE, NX><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
       else gik_solve_pair_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     }
   } else if constexpr (sizeof(T) == 4) {
     if (prm->flags & GIK_F_SCALAR_LANE) {
-      if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      if (wrist) gik_solve_kernel<T, MODE, NX, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+      else if (nx) gik_solve_kernel<T, MODE, NX><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
       else gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     } else {                                             // packed FFMA2 lane kernel (default for fp32)
-      if (nx) gik_solve_lane2_kernel<MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
+      if (wrist) gik_solve_lane2_kernel<MODE, NX, true><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
+      else if (nx) gik_solve_lane2_kernel<MODE, NX><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
       else gik_solve_lane2_kernel<MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, h->pt32, a);
     }
   } else {
-    if (nx) gik_solve_kernel<T, MODE, kNextageTZ><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    if (wrist) gik_solve_kernel<T, MODE, NX, true><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
+    else if (nx) gik_solve_kernel<T, MODE, NX><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
     else gik_solve_kernel<T, MODE, 0><<<blocks, GIK_THREADS, 0, st>>>(tab, a);
   }
   return (int)cudaGetLastError();
@@ -1188,8 +1226,10 @@ int gik_solve_launch_dims(gik_handle_t h, int elem_size, int64_t n, int32_t* blo
   if (g.err != cudaSuccess) return (int)g.err;
   int b = 0, l = 32, rc;
   bool pair = false;
-  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, 0, &b, &l, &pair);
-  else if (elem_size == 8) rc = choose_launch<double, MODE_BATCH>(h, n, 0, &b, &l, &pair);
+  gik_params_t dp;
+  gik_default_params(&dp);
+  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, 0, use_wrist<float>(h, &dp), &b, &l, &pair);
+  else if (elem_size == 8) rc = choose_launch<double, MODE_BATCH>(h, n, 0, use_wrist<double>(h, &dp), &b, &l, &pair);
   else return GIK_E_PARAM;
   if (rc) return rc;
   *blocks = b; *threads = GIK_THREADS;
@@ -1202,9 +1242,18 @@ const char* gik_solve_kernel_name(gik_handle_t h, int elem_size, int64_t n, int 
   if (g.err != cudaSuccess) return "";
   int b = 0, l = 32, rc;
   bool pair = false;
-  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, flags, &b, &l, &pair);
-  else rc = choose_launch<double, MODE_BATCH>(h, n, flags, &b, &l, &pair);
+  gik_params_t dp;
+  gik_default_params(&dp);
+  dp.flags = flags & GIK_F_CHOLESKY;
+  if (elem_size == 4) rc = choose_launch<float, MODE_BATCH>(h, n, flags, use_wrist<float>(h, &dp), &b, &l, &pair);
+  else rc = choose_launch<double, MODE_BATCH>(h, n, flags, use_wrist<double>(h, &dp), &b, &l, &pair);
   if (rc) return "";
+  const bool wrist = elem_size == 4 ? use_wrist<float>(h, &dp) : use_wrist<double>(h, &dp);
+  if (wrist) {
+    if (pair) return elem_size == 4 ? "gik_solve_pair_kernel<float, wrist>" : "gik_solve_pair_kernel<double, wrist>";
+    if (elem_size == 8) return "gik_solve_kernel<double, wrist>";
+    return (flags & GIK_F_SCALAR_LANE) ? "gik_solve_kernel<float, wrist>" : "gik_solve_lane2_kernel<wrist>";
+  }
   if (pair) return elem_size == 4 ? "gik_solve_pair_kernel<float>" : "gik_solve_pair_kernel<double>";
   if (elem_size == 8) return "gik_solve_kernel<double>";
   return (flags & GIK_F_SCALAR_LANE) ? "gik_solve_kernel<float>" : "gik_solve_lane2_kernel";

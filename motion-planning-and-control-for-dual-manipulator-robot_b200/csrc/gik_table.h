@@ -105,6 +105,10 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
                              (double)(T)av[0], (double)(T)av[1], (double)(T)av[2]};
       for (int i = 0; i < 6; ++i)
         for (int j = 0; j <= i; ++j) ac.g6[i * (i + 1) / 2 + j] = (T)(col[i] * col[j]);
+      // wrist centre in the hand frame: the tip joint's origin moved back along the tip axis by its own placement
+      // (t[6] = (0, 0, z) on spherical-wrist tables; unused otherwise)
+      const double tz = t.joint_p[chain[h][6]][2];
+      for (int i = 0; i < 3; ++i) ac.rw[i] = (T)(fi_p[i] - tz * av[i]);
     }
     for (int i = 0; i < 9; ++i) ac.hook_R[i] = (T)t.hook_R[h][i];
     for (int i = 0; i < 3; ++i) ac.hook_p[i] = (T)t.hook_p[h][i];
@@ -132,6 +136,7 @@ inline void build_packed_table(const DevTable<float>& d, PackedTable& p) {
     p.arm.finv_p[i] = F2(L.finv_p[i], R.finv_p[i]);
     p.arm.tip_lin[i] = F2(L.tip_lin[i], R.tip_lin[i]);
     p.arm.hook_p[i] = F2(L.hook_p[i], R.hook_p[i]);
+    p.arm.rw[i] = F2(L.rw[i], R.rw[i]);
   }
   for (int k = 0; k < 6; ++k) { p.lo[k] = F2(d.lo[1 + k], d.lo[7 + k]); p.hi[k] = F2(d.hi[1 + k], d.hi[7 + k]); }
   p.lo0 = d.lo[0]; p.hi0 = d.hi[0];

@@ -98,16 +98,25 @@ class GraspIK:
     # GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL / GIK_F_SCALAR_LANE (fp32: "lane" = packed FFMA2 kernel, "lane1" = scalar)
     _KERNEL_FLAGS = {None: 0, "auto": 0, "lane": 2, "pair": 4, "lane1": 2 | 8}
 
+    # Step form: by default an undamped step on a spherical-wrist table (Nextage) runs as two 3x3 solves per hand
+    # (gik_core.cuh "Spherical-wrist form"); `force_cholesky` (a solver attribute, or the "+chol" kernel suffix) keeps the
+    # general block-Cholesky form for A/B runs and tests.  GIK_F_CHOLESKY = 32.
+    force_cholesky = False
+
     def _params(self, eps, dt, max_iters, damping, kernel=None, early_stop=False) -> _cabi.GikParams:
+        chol = self.force_cholesky
+        if isinstance(kernel, str) and kernel.endswith("+chol"):
+            chol, kernel = True, (kernel[:-5] or None)
         if kernel not in self._KERNEL_FLAGS:
-            raise ValueError(f"kernel must be one of {list(self._KERNEL_FLAGS)}")
-        flags = self._KERNEL_FLAGS[kernel] | (16 if early_stop else 0)        # GIK_F_EARLY_STOP
+            raise ValueError(f"kernel must be one of {list(self._KERNEL_FLAGS)} (optionally with the suffix '+chol')")
+        flags = self._KERNEL_FLAGS[kernel] | (16 if early_stop else 0) | (32 if chol else 0)   # GIK_F_EARLY_STOP, GIK_F_CHOLESKY
         return _cabi.GikParams(float(eps), float(dt), float(damping), int(max_iters), flags)
 
     def kernel_name(self, n, dtype=torch.float32, kernel=None) -> str:
         """Kernel the batch solve launches for n problems (gik_solve_kernel_name); for reports."""
         esz = 4 if dtype == torch.float32 else 8
-        return self._lib.gik_solve_kernel_name(self._h, esz, int(n), self._KERNEL_FLAGS[kernel]).decode()
+        flags = self._params(1e-3, 1e-2, 1, 0.0, kernel).flags
+        return self._lib.gik_solve_kernel_name(self._h, esz, int(n), flags).decode()
 
     def _chk_dev(self, *ts):
         for t in ts:
@@ -480,10 +489,10 @@ def solve_host(self, q_init, pose, *, dtype=torch.float32, eps=EPSILON, dt=DT, m
             if tuple(t.shape) != shape or t.dtype != dt_ or not t.is_contiguous() or t.is_cuda or (B and not t.is_pinned()):
                 raise ValueError(f"out tensors must be pinned contiguous CPU tensors; expected {shape} {dt_}")
     else:
-        q_out = torch.empty((B, self.nq), dtype=dtype).pin_memory() if B else torch.empty((0, self.nq), dtype=dtype)
-        c_out = torch.empty((B,), dtype=torch.uint8).pin_memory() if B else torch.empty((0,), dtype=torch.uint8)
-        it_out = (torch.empty((B,), dtype=torch.int32).pin_memory() if B else torch.empty((0,), dtype=torch.int32)) if return_info else None
-        r_out = (torch.empty((B, 2), dtype=dtype).pin_memory() if B else torch.empty((0, 2), dtype=dtype)) if return_info else None
+        q_out = torch.empty((B, self.nq), dtype=dtype, pin_memory=True) if B else torch.empty((0, self.nq), dtype=dtype)
+        c_out = torch.empty((B,), dtype=torch.uint8, pin_memory=True) if B else torch.empty((0,), dtype=torch.uint8)
+        it_out = (torch.empty((B,), dtype=torch.int32, pin_memory=True) if B else torch.empty((0,), dtype=torch.int32)) if return_info else None
+        r_out = (torch.empty((B, 2), dtype=dtype, pin_memory=True) if B else torch.empty((0, 2), dtype=dtype)) if return_info else None
     if B == 0:
         return (q_out, c_out.view(torch.bool)) + ((SolveInfo(it_out, r_out),) if return_info else ())
     lock = self.__dict__.setdefault("_host_lock", threading.Lock())

@@ -54,6 +54,7 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
   if (rc) return rc;
   const T eps2 = (T)(prm->eps * prm->eps), dt = (T)prm->dt, lambda = (T)prm->damping;
   const bool generic = (prm->flags & 1) != 0;   // test hook: force the TZ = 0 instantiation
+  const bool no_wrist = (prm->flags & 2) != 0;  // test hook: keep the Cholesky step where the spherical-wrist step would run
   for (int64_t i = 0; i < n; ++i) {
     T q[kActive], cube[12], tgt[2][12], dq[kActive], rL = 0, rR = 0;
     for (int a = 0; a < kActive; ++a) q[a] = q_init[(int64_t)d.act_q[a] * n + i];
@@ -64,7 +65,9 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
     bool ok = false;
     for (;;) {
       // same specialisation rule as launch_solve() in csrc/gik_kernels.cu
-      if ((d.tzero & kNextageTZ) == kNextageTZ && !generic) ik_iteration<T, true, kNextageTZ>(d, q, tgt, lambda, dq, rL, rR);
+      const bool nx = (d.tzero & kNextageTZ) == kNextageTZ && !generic;
+      if (nx && lambda == T(0) && !no_wrist) ik_iteration<T, true, kNextageTZ, true>(d, q, tgt, lambda, dq, rL, rR);
+      else if (nx) ik_iteration<T, true, kNextageTZ>(d, q, tgt, lambda, dq, rL, rR);
       else ik_iteration<T, true, 0>(d, q, tgt, lambda, dq, rL, rR);
       ok = (rL < eps2) && (rR < eps2) && (it < prm->max_iters);
       if (ok || it >= prm->max_iters) break;

@@ -98,14 +98,18 @@ def _oracle_batch(c_oracle, table_c, n, seed, box="workspace", yaw=False):
     return P, c_oracle.solve(table_c, np.zeros((n, 15)), P)
 
 
-def _assert_q_close(q, q_ref, tol, frac=0.995, tol_outlier=5e-3):
+def _assert_q_close(q, q_ref, tol, frac=0.995, tol_outlier=5e-3, n_far=None):
     """Undamped pinv flow: a trajectory that brushes a kinematic singularity (arm stretched towards the edge of
-    the workspace) amplifies round-off by ~1/sigma_min per step, so two fp64 implementations of the SAME iteration
-    (numpy pinv vs the C oracle's Jacobi SVD vs the kernel's Cholesky) agree to ~1e-15 on almost every problem and
-    to ~1e-4 on a rare outlier that still converges to the same tolerance.  Assert both."""
+    the workspace) amplifies round-off by ~1/sigma_min per step, so two implementations of the SAME iteration
+    (numpy pinv vs the C oracle's Jacobi SVD vs the kernel's solves) agree to ~1e-15 (fp64) on almost every problem and
+    land a rare outlier elsewhere on the arm's 1-dimensional self-motion manifold -- converged to the same tolerance,
+    with the same flag.  Measured on 65,536 problems (profiles/parity_r2.json): 0.04-0.05 % of the problems converged in
+    both differ by more than 1e-3.  Assert the bulk, and that at most `n_far` (default: 0.2 %, at least 1) lie beyond
+    `tol_outlier`."""
     d = np.abs(q - q_ref).max(axis=1)
     assert np.quantile(d, frac) < tol, np.sort(d)[-5:]
-    assert d.max() < tol_outlier, np.sort(d)[-5:]
+    n_far = max(1, int(2e-3 * len(d))) if n_far is None else n_far
+    assert (d >= tol_outlier).sum() <= n_far, np.sort(d)[-5:]
 
 
 def test_solve_fp64_matches_oracle(solver, table_c, c_oracle):
@@ -243,6 +247,43 @@ def test_pair_kernel_equals_lane_kernel(solver, dtype):
         assert torch.equal(pa[1], pb[1]) and torch.equal(pa[2], pb[2]) and torch.equal(pa[0], pb[0])
     else:
         assert (pa[1] == pb[1]).float().mean() >= 0.9 and (pa[0] - pb[0]).abs()[:, :, (pa[1] == pb[1])].max() < 2e-3
+
+
+def test_wrist_form_equals_cholesky_form(solver, table):
+    # The undamped step on the Nextage table runs as two 3x3 solves per hand at the wrist centre (default); "+chol"
+    # keeps the general 6x6 block-Cholesky form.  Same pinv(J) e: in fp64 the two agree at round-off on every problem
+    # that does not brush a singularity; in fp32 the wrist form is the better conditioned one (cond(A) instead of
+    # cond(A)^2), so the comparison is statistical there.
+    n = 20000
+    P = _t(make_poses(n, 63), torch.float64).t().contiguous()
+    q0 = torch.zeros((15, n), dtype=torch.float64, device="cuda:0")
+    assert "wrist" in solver.kernel_name(n, torch.float64) and "wrist" not in solver.kernel_name(n, torch.float64, "pair+chol")
+    a = solver.solve_soa(q0, P)
+    b = solver.solve_soa(q0, P, kernel="pair+chol")
+    assert (a[1] == b[1]).float().mean() >= 0.999
+    both = (a[1] & b[1]).bool()
+    d = (a[0][:, both] - b[0][:, both]).abs().max(dim=0).values
+    assert torch.quantile(d, 0.99) < 1e-9 and (a[2][both] == b[2][both]).float().mean() >= 0.998
+    # lane / pair mappings of the wrist form: bit-identical in fp64
+    c = solver.solve_soa(q0, P, kernel="lane")
+    for x, y in zip(a, c):
+        assert torch.equal(x, y)
+    # damping > 0 always takes the Cholesky form, and lambda -> 0 joins the wrist form continuously
+    e = solver.solve_soa(q0[:, :2000].contiguous(), P[:, :2000].contiguous(), damping=1e-13, max_iters=50)
+    f = solver.solve_soa(q0[:, :2000].contiguous(), P[:, :2000].contiguous(), max_iters=50)
+    assert (e[0] - f[0]).abs().max() < 1e-7
+    # fp32, all three mappings
+    P32, q32 = P.float(), q0.float()
+    ref = solver.solve_soa(q32, P32, kernel="lane+chol")
+    for kern in ("lane", "pair", "lane1"):
+        g = solver.solve_soa(q32, P32, kernel=kern)
+        assert (g[1] == ref[1]).float().mean() >= 0.998
+        both = (g[1] & ref[1]).bool()
+        d = (g[0][:, both] - ref[0][:, both]).abs().max(dim=0).values
+        assert torch.quantile(d, 0.995) < 1e-3 and (g[2][both] - ref[2][both]).abs().float().quantile(0.995) <= 2
+        # agreement with the fp64 result: the wrist form must not be worse than the Cholesky form
+        bad_w = (g[1] != a[1]).sum().item(); bad_c = (ref[1] != a[1]).sum().item()
+        assert bad_w <= bad_c + 2, (kern, bad_w, bad_c)
 
 
 def test_scatter_entry_on_one_gpu(solver):
@@ -544,7 +585,7 @@ def test_fp64_large_batch_instantiation_equals_lane_kernel(solver):
     # including edges with nothing to march, which leave a lane pair idle while the queue still has work.
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     n = 16 * 8 * sms + 517
-    assert solver.kernel_name(n, torch.float64) == "gik_solve_pair_kernel<double>"
+    assert solver.kernel_name(n, torch.float64).startswith("gik_solve_pair_kernel<double")
     P = _t(make_poses(n, 71)).t().contiguous()
     q0 = torch.zeros((15, n), dtype=torch.float64, device="cuda:0")
     a = solver.solve_soa(q0, P)
