@@ -231,18 +231,31 @@ int gik_collision_sel_f32(gik_handle_t h, int64_t n, int64_t n_sel, const int64_
 int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_t* sel, const double* q,
                           const double* cube_pose, uint8_t* colliding, void* stream);
 
-/* K3 + the collision term in ONE stream-ordered call without host synchronisation: the descent loop, then
- * success[i] = converged[i] && !collision(q_out[:, i]) with collision() evaluated only on the converged problems
- * (device-side compaction).  This is the reference's predicate (inverse_geometry.py:70, 97-98) evaluated ONCE at the
- * configuration the descent stopped at; the reference additionally keeps descending while a converged iterate
- * collides (re-testing after every update) -- GraspIK.solve_success_soa(descend_while_colliding=True) reproduces that
- * tail with single-update re-entry rounds.  scratch: device, (n + 1) int64.  converged must not be NULL. */
+/* K3 + the collision term: the reference's FULL success predicate (inverse_geometry.py:70, 97-98) in ONE stream-ordered
+ * call without host synchronisation.
+ *   1. the descent loop (as gik_solve_*), stopping at the first iterate with both residuals < eps;
+ *   2. success[i] = converged[i] && !collision(q_out[:, i]), collision() evaluated only on the converged problems
+ *      (device-side compaction: the predicate's short-circuit);
+ *   3. the reference KEEPS DESCENDING while a converged iterate collides, re-testing collision() after every update
+ *      until an iterate is free (success, that q, that iteration count) or max_iters is reached (failure, q after
+ *      max_iters updates).  The converged-but-colliding problems are continued to the cap by a second launch of the
+ *      solve kernel, and a warp-per-problem kernel then decides each one: a pair of solids that still intersects after
+ *      erosion by the (bounded) displacement of the remaining descent collides on every iterate -- the problem fails
+ *      with the final q, as in the reference; otherwise the descent is replayed from the converged iterate with the
+ *      undecided pairs tested on every iterate.  Same decisions as the reference's loop.
+ * params.flags & GIK_F_NO_DESCEND stops after step 2 (the predicate evaluated once, at the configuration the descent
+ * stopped at: differs only where further descent would have freed a collision, and in the q of failed problems).
+ * On return converged[i] = 1 iff the loop broke at q_out[:, i] (so converged == success except with GIK_F_NO_DESCEND,
+ * where converged keeps step 1's flag); iters / resid describe q_out.  success, converged, iters, resid must not be
+ * NULL.  scratch: device memory of gik_solve_success_scratch_bytes(h, n, elem_size) bytes. */
+#define GIK_F_NO_DESCEND 64
+size_t gik_solve_success_scratch_bytes(gik_handle_t h, int64_t n, int elem_size);
 int gik_solve_success_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* params,
                           float* q_out, uint8_t* success, uint8_t* converged, int32_t* iters, float* resid,
-                          int64_t* scratch, void* stream);
+                          void* scratch, void* stream);
 int gik_solve_success_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* params,
                           double* q_out, uint8_t* success, uint8_t* converged, int32_t* iters, double* resid,
-                          int64_t* scratch, void* stream);
+                          void* scratch, void* stream);
 
 /* Replaces `distanceToObstacle(robot, q) >= threshold` (tools.py:38-51 with path.py:61-62): clear [n] = 1 when every
  * pair whose second geometry is the table or the obstacle is at least `threshold` apart. */

@@ -6,7 +6,7 @@
 The arithmetic lives in csrc/ (CUDA, sm_100a) behind the C ABI of include/gik.h; nothing here falls back to
 the CPU."""
 from .model import KinematicTable, from_pinocchio, from_urdf, nextage_table          # noqa: F401
-from .scene import CollisionScene, nextage_scene, scene_from_urdf                               # noqa: F401
+from .scene import CollisionScene, nextage_scene, scene_from_pinocchio, scene_from_urdf                               # noqa: F401
 from .ops import (DT, EPSILON, MAX_ITERS, GraspIK, SolveInfo, as_pose12, bytes_per_solve,  # noqa: F401
                   default_solver, flops_per_iter, fma_peak_tflops)
 from .inverse_geometry import apply_collision, computeqgrasppose, computeqgrasppose_batch, solver_for  # noqa: F401

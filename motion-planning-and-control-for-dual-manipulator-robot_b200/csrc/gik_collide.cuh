@@ -210,16 +210,25 @@ GIK_HD bool erode_shape(Shape<T>& S, T shrink) {
   return S.s0 > T(0) && (S.type == GEOM_SPHERE || S.s1 > T(0)) && (S.type != GEOM_BOX || S.s2 > T(0));
 }
 
+// smallest half extent of a shape: how much erosion it survives
+template <typename T>
+GIK_HD T min_extent(const Shape<T>& S) {
+  if (S.type == GEOM_SPHERE) return S.s0;
+  if (S.type == GEOM_BOX) return min_(S.s0, min_(S.s1, S.s2));
+  return min_(S.s0, S.s1);
+}
+
 // Narrow phase of one pair.  margin >= 0: does (A inflated by margin) intersect B  (collision: 0; clearance: the
-// threshold).  margin < 0: do A and B, each ERODED by |margin| / 2, intersect -- a PERSISTENT collision: the two solids
-// keep intersecting under any relative displacement of their points smaller than |margin| (used to settle the
+// threshold).  margin < 0: does the THICKER of the two solids, eroded by |margin|, still intersect the other one -- a
+// PERSISTENT collision: a point x of that intersection has its |margin|-ball inside the eroded solid's original, so the
+// two solids keep intersecting under any relative displacement of their points of at most |margin| (used to settle the
 // reference's keep-descending-while-colliding tail without testing every iterate, gik_collide_impl.cuh).
 template <typename T>
 GIK_HD bool narrow_hits(const DevGeom<T>& ga, const T* Ma, const DevGeom<T>& gb, const T* Mb, T margin) {
   Shape<T> A = make_shape(ga, Ma), B = make_shape(gb, Mb);
   if (margin < T(0)) {
-    const T sh = T(-0.5) * margin;
-    if (!erode_shape(A, sh) || !erode_shape(B, sh)) return false;
+    const bool a_thicker = min_extent(A) >= min_extent(B);
+    if (!erode_shape(a_thicker ? A : B, -margin)) return false;
     return gjk_intersect(A, B, T(0));
   }
   return gjk_intersect(A, B, margin);

@@ -124,6 +124,269 @@ __global__ void __launch_bounds__(256) gik_compact_converged_kernel(int64_t n, c
   }
 }
 
+// pending = converged && colliding && iterations left: the problems on which the reference keeps descending
+// (inverse_geometry.py:70 -- the predicate stays False while collision(q) holds).  success[] holds converged && !colliding.
+__global__ void __launch_bounds__(256) gik_compact_pending_kernel(int64_t n, const uint8_t* __restrict__ conv,
+                                                                  const uint8_t* __restrict__ success,
+                                                                  const int32_t* __restrict__ iters, int max_iters,
+                                                                  int64_t* __restrict__ count, int64_t* __restrict__ sel) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + lane;
+    const bool c = i < n && conv[i] != 0 && success[i] == 0 && iters[i] < max_iters;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    long long base = 0;
+    if (lane == 0 && m) base = (long long)atomicAdd((unsigned long long*)count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (c) sel[base + __popc(m & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// tree FK of one configuration by one warp (level by level, one joint per lane) into oMi[nq][12]; q_of(j) = q_j
+template <typename T, typename QF>
+__device__ __forceinline__ void warp_tree_fk(const DevScene<T>* sc, int lane, QF q_of, T (*oMi)[12]) {
+  const int nq = sc->tree.nq;
+  T L[12];
+  int par = -1, dep = -1;
+  if (lane < nq) {
+    joint_placement(sc->tree, lane, (const T*)nullptr, q_of(lane), L);
+    par = sc->tree.parent[lane]; dep = sc->tree.depth[lane];
+  }
+  for (int d = 0; d <= sc->tree.max_depth; ++d) {
+    if (dep == d) {
+      if (par < 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) oMi[lane][k] = L[k];
+      } else {
+        se3_mul12(&oMi[par][0], L, &oMi[lane][0]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// world placement of geometry g: oMi[parent] * placement (pin.updateGeometryPlacements); the cube takes the problem's pose
+template <typename T>
+__device__ __forceinline__ void place_geom(const DevScene<T>* sc, int g, const T* cube12, const T (*oMi)[12], T* out) {
+  const DevGeom<T>& G = sc->g[g];
+  T P[12];
+  if (g == sc->cube_geom && cube12) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P[k] = cube12[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P[k] = G.R[k];
+    P[9] = G.p[0]; P[10] = G.p[1]; P[11] = G.p[2];
+  }
+  if (G.joint >= 0) se3_mul12(&oMi[G.joint][0], P, out);
+  else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) out[k] = P[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's keep-descending-while-colliding tail (inverse_geometry.py:70, 97-98), ONE WARP PER PENDING PROBLEM.
+//
+// A pending problem converged at iteration it_c in configuration q_c and collides there.  The reference goes on
+// descending -- the residual keeps shrinking, so every later iterate passes the residual test -- and re-tests
+// collision(q) on every iterate until one is free (success) or the cap is reached (failure, q after max_iters updates).
+// The continuation launch of the solve kernel has already produced that last configuration q_f.  Between q_c and q_f
+// every point of the robot moves by a few millimetres at most, which settles almost every pair for ALL iterates at once:
+//   * delta_ab = safety * (disp_a + disp_b) + floor bounds the relative displacement of geometries a, b over the tail
+//     (disp_g = |p_g(q_f) - p_g(q_c)| + ||R_g(q_f) - R_g(q_c)||_F * bounding radius; the iterates lie between q_c and q_f
+//     on a path that is straight to first order -- e_k = (1 - dt)^k e_c -- hence the safety factor);
+//   * a pair whose shapes still intersect when both are ERODED by delta/2 collides on every iterate: the problem fails
+//     with q = q_f, exactly what the reference returns, and no iterate needs testing (PERSISTENT);
+//   * a pair that does not intersect even when INFLATED by delta is free on every iterate and is dropped;
+//   * what is left (typically the fingers against the cube face they sit 1 mm from) is UNDECIDED: the warp then replays
+//     the descent from q_c -- lanes 0 / 1 run the two hands of the pair mapping -- and tests just those pairs on every
+//     iterate, stopping at the first iterate that is converged and free: the reference's decision, iterate by iterate.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool WRIST>
+__global__ void __launch_bounds__(kCollideWarps * 32)
+gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa,
+                const uint8_t* __restrict__ pb, int n_pairs, int64_t n, const int64_t* __restrict__ sel,
+                const int64_t* __restrict__ n_sel_dev, const T* __restrict__ pose, const T* __restrict__ q_fin,
+                const T* __restrict__ resid_fin, T* q, uint8_t* success, uint8_t* conv, int32_t* iters, T* resid,
+                T eps2, T dt, T lambda, int max_iters, T safety, unsigned long long* queue, unsigned long long* stats) {
+  __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
+  __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
+  __shared__ T s_disp[kCollideWarps][GIK_MAX_GEOMS];
+  __shared__ T s_q[kCollideWarps][GIK_MAX_NQ];
+  __shared__ uint16_t s_cand[kCollideWarps][kMaxCand];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nq = sc->tree.nq, ng = sc->n_geoms;
+  const int64_t count = min(n, (int64_t)*n_sel_dev);
+  const T kFloor = sizeof(T) == 4 ? T(2e-5) : T(1e-9);     // round-off of the placements themselves
+  const int h = lane & 1, off = 1 + 6 * h;
+  const ArmConst<T>& ac = tab.arm[h];
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if ((int64_t)item >= count) break;
+    const int64_t i = sel[item];
+    T cube[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cube[k] = __ldg(pose + (int64_t)k * n + i);
+    // ---- displacement of every geometry between q_c and q_f
+    warp_tree_fk(sc, lane, [&](int j) { return q_fin[(int64_t)j * n + i]; }, s_oMi[w]);
+    T Pf[2][12];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int g = lane + 32 * sl;
+      if (g < ng) place_geom(sc, g, cube, s_oMi[w], Pf[sl]);
+    }
+    __syncwarp();
+    if (lane < nq) s_q[w][lane] = q[(int64_t)lane * n + i];
+    __syncwarp();
+    warp_tree_fk(sc, lane, [&](int j) { return s_q[w][j]; }, s_oMi[w]);
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const int g = lane + 32 * sl;
+      if (g < ng) {
+        T Pc[12];
+        place_geom(sc, g, cube, s_oMi[w], Pc);
+        T dR = T(0), dp = T(0);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const T d = Pc[k] - Pf[sl][k]; dR += d * d; }
+#pragma unroll
+        for (int k = 9; k < 12; ++k) { const T d = Pc[k] - Pf[sl][k]; dp += d * d; }
+        s_disp[w][g] = sqrt_(dp) + sqrt_(dR) * sc->g[g].bound;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_oMg[w][g][k] = Pc[k];
+      }
+    }
+    __syncwarp();
+    // ---- broad phase with the displacement margin, candidates compacted
+    int n_cand = 0;
+    for (int k0 = 0; k0 < n_pairs; k0 += 32) {
+      const int k = k0 + lane;
+      bool pass = false;
+      if (k < n_pairs) {
+        const int a = pa[k], b = pb[k];
+        const T* Ma = &s_oMg[w][a][0];
+        const T* Mb = &s_oMg[w][b][0];
+        const T dx = Ma[9] - Mb[9], dy = Ma[10] - Mb[10], dz = Ma[11] - Mb[11];
+        const T reach = sc->g[a].bound + sc->g[b].bound + safety * (s_disp[w][a] + s_disp[w][b]) + kFloor;
+        pass = dx * dx + dy * dy + dz * dz <= reach * reach;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (pass && n_cand + __popc(m & ((1u << lane) - 1u)) < kMaxCand) s_cand[w][n_cand + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+      n_cand = min(n_cand + __popc(m), kMaxCand);
+    }
+    __syncwarp();
+    // ---- narrow phase: persistent / undecided (the undecided ones are compacted in place at the front of the list)
+    bool persistent = false;
+    int n_und = 0;
+    for (int c0 = 0; c0 < n_cand; c0 += 32) {
+      bool pers = false, und = false;
+      int k = 0;
+      if (c0 + lane < n_cand) {
+        k = s_cand[w][c0 + lane];
+        const int a = pa[k], b = pb[k];
+        const T delta = safety * (s_disp[w][a] + s_disp[w][b]) + kFloor;
+        pers = narrow_hits(sc->g[a], &s_oMg[w][a][0], sc->g[b], &s_oMg[w][b][0], -delta);
+        if (!pers) und = narrow_hits(sc->g[a], &s_oMg[w][a][0], sc->g[b], &s_oMg[w][b][0], delta);
+      }
+      persistent = persistent || __any_sync(0xffffffffu, pers);
+      const unsigned m = __ballot_sync(0xffffffffu, und);
+      __syncwarp();
+      if (und) s_cand[w][n_und + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;    // n_und <= c0: never ahead of the reads
+      n_und += __popc(m);
+      __syncwarp();
+    }
+    if (persistent) {
+      // collides on every iterate: the loop runs to the cap, q after max_iters updates, success = False
+      if (lane < nq) q[(int64_t)lane * n + i] = q_fin[(int64_t)lane * n + i];
+      if (lane == 0) {
+        success[i] = 0; conv[i] = 0; iters[i] = max_iters;
+        resid[i] = resid_fin[i]; resid[n + i] = resid_fin[n + i];
+        if (stats) atomicAdd(stats + 0, 1ull);
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- replay the descent from q_c, testing the undecided pairs on every iterate
+    T qh[7], tgt[12];
+    {
+      qh[0] = s_q[w][tab.act_q[0]];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) qh[1 + k] = s_q[w][tab.act_q[off + k]];
+      hook_target(ac, cube, tgt);
+    }
+    int it = iters[i];
+    unsigned long long trips = 0;
+    for (;;) {
+      T r = T(0), r_o = T(0), kappa = T(0), dqa[6];
+      if (lane < 2) {
+        T cs[kActive], sn[kActive], Sy, Sz;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sincos_<true>(qh[k], sn[k], cs[k]);
+        HandState<T> hs;
+        WristState<T> wst;
+        if constexpr (WRIST) hand_wrist_phase1<T, 0, kNextageTZ>(ac, cs, sn, tgt, wst, Sy, Sz, r);
+        else hand_phase1<T, 0, 0, false>(ac, cs, sn, tgt, lambda, hs, Sy, Sz, r);
+        const T Sy_o = __shfl_xor_sync(0x3u, Sy, 1), Sz_o = __shfl_xor_sync(0x3u, Sz, 1);
+        r_o = __shfl_xor_sync(0x3u, r, 1);
+        kappa = h ? chest_rate(Sy_o, Sz_o, Sy, Sz) : chest_rate(Sy, Sz, Sy_o, Sz_o);
+        if constexpr (WRIST) hand_wrist_phase2(wst, kappa, dqa);
+        else hand_phase2(hs, kappa, dqa);
+      }
+      const bool pass0 = (r < eps2) && (r_o < eps2) && (it < max_iters);
+      const bool pass = __shfl_sync(0xffffffffu, (int)pass0, 0) != 0;
+      bool collide = false;
+      if (pass) {
+        if (lane < 2) {
+          if (h == 0) s_q[w][tab.act_q[0]] = qh[0];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s_q[w][tab.act_q[off + k]] = qh[1 + k];
+        }
+        __syncwarp();
+        warp_tree_fk(sc, lane, [&](int j) { return s_q[w][j]; }, s_oMi[w]);
+        for (int c0 = 0; c0 < n_und && !collide; c0 += 32) {
+          bool hit = false;
+          if (c0 + lane < n_und) {
+            const int k = s_cand[w][c0 + lane];
+            const int a = pa[k], b = pb[k];
+            T Ma[12], Mb[12];
+            place_geom(sc, a, cube, s_oMi[w], Ma);
+            place_geom(sc, b, cube, s_oMi[w], Mb);
+            hit = narrow_hits(sc->g[a], Ma, sc->g[b], Mb, T(0));
+          }
+          collide = __any_sync(0xffffffffu, hit);
+        }
+        __syncwarp();
+      }
+      const bool stop_ok = pass && !collide;
+      const bool stop_cap = it >= max_iters;
+      if (stop_ok || stop_cap) {
+        if (lane < 2) {                      // the configuration the loop stopped at
+          if (h == 0) s_q[w][tab.act_q[0]] = qh[0];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) s_q[w][tab.act_q[off + k]] = qh[1 + k];
+          resid[(int64_t)h * n + i] = sqrt_(r);
+        }
+        __syncwarp();
+        if (lane < nq) q[(int64_t)lane * n + i] = s_q[w][lane];
+        if (lane == 0) {
+          success[i] = stop_ok ? 1 : 0; conv[i] = stop_ok ? 1 : 0; iters[i] = it;
+          if (stats) { atomicAdd(stats + 1, 1ull); atomicAdd(stats + 2, trips); if (stop_ok) atomicAdd(stats + 3, 1ull); }
+        }
+        __syncwarp();
+        break;
+      }
+      if (lane < 2) {
+        qh[0] = min_(max_(tab.lo[0], qh[0] + dt * kappa), tab.hi[0]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) qh[1 + k] = min_(max_(tab.lo[off + k], qh[1 + k] + dt * dqa[k]), tab.hi[off + k]);
+      }
+      ++it; ++trips;
+    }
+  }
+}
+
 }  // namespace gik
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -175,26 +438,95 @@ int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int l
 
 }  // namespace
 
-// K3 + collision in one stream-ordered call, no host synchronisation: solve, compact the converged problems on the
-// device, test exactly those (the predicate's short-circuit) and write success = converged && !colliding.
+// scratch layout of gik_solve_success_* (bytes, 256-aligned blocks): two index lists with their device-side counts, the
+// continuation's outputs (q_f, residuals, flags, iteration counts), the tail kernel's work queue and counters
+struct SuccessScratch {
+  int64_t *sel1, *sel2;        // [n + 1] each: count at [0], list from [1]
+  void *q_fin, *resid_fin;     // [nq][n], [2][n] of T
+  uint8_t* flag_fin;           // [n]
+  int32_t* iters_fin;          // [n]
+  unsigned long long* queue;   // [1] + stats [4]
+  size_t bytes;
+};
+static SuccessScratch carve_scratch(void* base, int64_t n, int nq, int esz) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  SuccessScratch s{};
+  size_t o = 0;
+  char* b = (char*)base;
+  s.sel1 = (int64_t*)(b + o); o += up((size_t)(n + 1) * 8);
+  s.sel2 = (int64_t*)(b + o); o += up((size_t)(n + 1) * 8);
+  s.q_fin = b + o; o += up((size_t)nq * n * esz);
+  s.resid_fin = b + o; o += up((size_t)2 * n * esz);
+  s.flag_fin = (uint8_t*)(b + o); o += up((size_t)n);
+  s.iters_fin = (int32_t*)(b + o); o += up((size_t)n * 4);
+  s.queue = (unsigned long long*)(b + o); o += up(8 * 8);
+  s.bytes = o;
+  return s;
+}
+
+// K3 + the collision term in ONE stream-ordered call, no host synchronisation (inverse_geometry.py:70, 97-98):
+//   1. the descent loop (stops at the first iterate with both residuals < eps);
+//   2. the converged problems are compacted on the device and tested: success = converged && !collision(q);
+//   3. [unless GIK_F_NO_DESCEND] the converged-but-colliding problems are the ones the reference keeps descending on:
+//      a continuation launch of the solve kernel runs them to the iteration cap (q_f), and gik_tail_kernel decides each
+//      one -- persistent collision (fails with q_f), or a replay that tests the undecided pairs iterate by iterate.
 template <typename T>
 int solve_success_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const gik_params_t* prm, T* q_out,
-                      uint8_t* success, uint8_t* conv, int32_t* iters, T* resid, int64_t* scratch, void* stream) {
+                      uint8_t* success, uint8_t* conv, int32_t* iters, T* resid, void* scratch, void* stream) {
   if (bad_handle(h)) return GIK_E_HANDLE;
   if (!h->scene) return GIK_E_NOSCENE;
-  if (n > 0 && (!success || !conv || !scratch)) return GIK_E_NULL;
+  if (n > 0 && (!success || !conv || !scratch || !iters || !resid)) return GIK_E_NULL;
   int rc = solve_api<T>(h, n, q_init, pose, prm, q_out, conv, iters, resid, stream);
   if (rc || n == 0) return rc;
   DeviceGuard g(h->device);
   if (g.err != cudaSuccess) return (int)g.err;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int64_t), st);
+  const int nq = h->host.nq;
+  SuccessScratch sc = carve_scratch(scratch, n, nq, (int)sizeof(T));
+  cudaError_t e = cudaMemsetAsync(sc.sel1, 0, sizeof(int64_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(sc.sel2, 0, sizeof(int64_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(sc.queue, 0, 8 * 8, st);
   if (e != cudaSuccess) return (int)e;
   int64_t blocks = (n + 255) / 256;
   if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
-  gik::gik_compact_converged_kernel<<<(int)blocks, 256, 0, st>>>(n, conv, success, scratch, scratch + 1);
+  gik::gik_compact_converged_kernel<<<(int)blocks, 256, 0, st>>>(n, conv, success, sc.sel1, sc.sel1 + 1);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-  return collide_api<T>(h, n, q_out, pose, 0, 0.0, 1, success, stream, scratch + 1, 0, scratch);
+  rc = collide_api<T>(h, n, q_out, pose, 0, 0.0, 1, success, stream, sc.sel1 + 1, 0, sc.sel1);
+  if (rc || (prm->flags & GIK_F_NO_DESCEND)) return rc;
+  // ---- the tail
+  gik::gik_compact_pending_kernel<<<(int)blocks, 256, 0, st>>>(n, conv, success, iters, prm->max_iters, sc.sel2, sc.sel2 + 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  {
+    SolveArgs<T> a{};
+    a.q_init = q_out; a.pose = pose; a.iters = sc.iters_fin; a.resid = (T*)sc.resid_fin;
+    a.q_dst[0] = (T*)sc.q_fin; a.conv_dst[0] = sc.flag_fin; a.n_dst = 1; a.out_off = 0;
+    a.n = n;
+    set_soa(a, n, n);
+    a.sel = sc.sel2 + 1; a.n_sel = sc.sel2; a.it0 = iters;
+    gik_params_t p2 = *prm;
+    p2.flags &= ~GIK_F_EARLY_STOP;
+    rc = launch_solve<T, MODE_BATCH>(h, a, &p2, stream, /*force=*/true);
+    if (rc) return rc;
+  }
+  gik_scene_dev* sd = h->scene;
+  const uint8_t* pa = sd->pairs;
+  int64_t tb = (n + gik::kCollideWarps - 1) / gik::kCollideWarps;
+  const int64_t cap = (int64_t)h->sm_count * 12;
+  if (tb > cap) tb = cap;
+  const T safety = (T)1.5;
+  const bool wrist = use_wrist<T>(h, prm);
+  const T eps2 = (T)(prm->eps * prm->eps);
+  if (wrist)
+    gik::gik_tail_kernel<T, true><<<(int)tb, gik::kCollideWarps * 32, 0, st>>>(
+        table_of<T>(h), scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[0], n, sc.sel2 + 1, sc.sel2, pose, (const T*)sc.q_fin,
+        (const T*)sc.resid_fin, q_out, success, conv, iters, resid, eps2, (T)prm->dt, (T)prm->damping, prm->max_iters, safety,
+        sc.queue, sc.queue + 1);
+  else
+    gik::gik_tail_kernel<T, false><<<(int)tb, gik::kCollideWarps * 32, 0, st>>>(
+        table_of<T>(h), scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[0], n, sc.sel2 + 1, sc.sel2, pose, (const T*)sc.q_fin,
+        (const T*)sc.resid_fin, q_out, success, conv, iters, resid, eps2, (T)prm->dt, (T)prm->damping, prm->max_iters, safety,
+        sc.queue, sc.queue + 1);
+  return (int)cudaGetLastError();
 }
 
 extern "C" {
@@ -253,12 +585,16 @@ int gik_collision_sel_f64(gik_handle_t h, int64_t n, int64_t n_sel, const int64_
   return collide_api<double>(h, n, q, cube, 0, 0.0, 0, out, s, sel, n_sel);
 }
 int gik_solve_success_f32(gik_handle_t h, int64_t n, const float* q_init, const float* pose, const gik_params_t* p, float* q_out,
-                          uint8_t* success, uint8_t* conv, int32_t* iters, float* resid, int64_t* scratch, void* s) {
+                          uint8_t* success, uint8_t* conv, int32_t* iters, float* resid, void* scratch, void* s) {
   return solve_success_api<float>(h, n, q_init, pose, p, q_out, success, conv, iters, resid, scratch, s);
 }
 int gik_solve_success_f64(gik_handle_t h, int64_t n, const double* q_init, const double* pose, const gik_params_t* p, double* q_out,
-                          uint8_t* success, uint8_t* conv, int32_t* iters, double* resid, int64_t* scratch, void* s) {
+                          uint8_t* success, uint8_t* conv, int32_t* iters, double* resid, void* scratch, void* s) {
   return solve_success_api<double>(h, n, q_init, pose, p, q_out, success, conv, iters, resid, scratch, s);
+}
+size_t gik_solve_success_scratch_bytes(gik_handle_t h, int64_t n, int elem_size) {
+  if (bad_handle(h) || n < 0 || (elem_size != 4 && elem_size != 8)) return 0;
+  return carve_scratch(nullptr, n, h->host.nq, elem_size).bytes;
 }
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double thr, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 1, thr, 1, out, s); }
 int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double thr, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 1, thr, 1, out, s); }

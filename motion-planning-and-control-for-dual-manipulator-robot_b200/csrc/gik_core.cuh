@@ -283,6 +283,31 @@ GIK_HD F2 max_(F2 a, F2 b) { return F2(max_(a.x, b.x), max_(a.y, b.y)); }
 GIK_HD F2 min_(F2 a, F2 b) { return F2(min_(a.x, b.x), min_(a.y, b.y)); }
 GIK_HD F2 rsqrt_(F2 a) { return F2(rsqrt_(a.x), rsqrt_(a.y)); }
 GIK_HD F2 rcp_(F2 a) { return F2(rcp_(a.x), rcp_(a.y)); }
+GIK_HD F2 sqrt_(F2 a) { return F2(sqrt_(a.x), sqrt_(a.y)); }
+GIK_HD F2 abs_(F2 a) { return F2(fabsf(a.x), fabsf(a.y)); }
+// per-half predicates and selects (FSETP / FSEL on the ALU pipe, which the FMA-bound loop has to spare)
+struct B2 { bool x, y; };
+GIK_HD B2 gt_(F2 a, F2 b) { return {a.x > b.x, a.y > b.y}; }
+GIK_HD B2 ge_(F2 a, F2 b) { return {a.x >= b.x, a.y >= b.y}; }
+GIK_HD B2 lt_(F2 a, F2 b) { return {a.x < b.x, a.y < b.y}; }
+GIK_HD F2 sel_(B2 c, F2 a, F2 b) { return F2(c.x ? a.x : b.x, c.y ? a.y : b.y); }
+// atan2_pos on both halves: the same degree-7 polynomial as the scalar fp32 form, evaluated with packed FMAs
+GIK_HD F2 atan2_pos(F2 y, F2 x) {
+  const F2 ax = abs_(x);
+  const F2 mn = min_(y, ax), mx = max_(max_(y, ax), F2(1e-30f));
+  const F2 a = mn * rcp_(mx), t = a * a;
+  F2 p = F2(3.8667389163e-03f);
+  p = p * t + F2(-2.0026747651e-02f);
+  p = p * t + F2(4.8914321553e-02f);
+  p = p * t + F2(-8.0096817182e-02f);
+  p = p * t + F2(1.0865759085e-01f);
+  p = p * t + F2(-1.4257044926e-01f);
+  p = p * t + F2(1.9998681172e-01f);
+  p = p * t + F2(-3.3333323101e-01f);
+  F2 r = (a * t) * p + a;
+  r = sel_(gt_(y, ax), F2(1.57079632679489662f) - r, r);
+  return sel_(lt_(x, F2(0.0f)), F2(3.14159265358979324f) - r, r);
+}
 template <> struct Num<F2> { static constexpr float kPivotFloor = 1e-30f; static constexpr float kRcpCap = 1e12f; };
 
 // FAST = MUFU-based sin/cos (abs error ~5e-7 on [-pi, pi]); accurate otherwise.
@@ -411,6 +436,58 @@ GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
   e[3] = wx; e[4] = wy; e[5] = wz;
 }
 
+// Both hands at once (packed fp32 lane kernel): the two log6 evaluations are the same straight-line sequence on
+// different data, so they run on the halves of F2 values -- packed FMAs, per-half MUFU results and selects.  The series
+// forms of alpha / beta are evaluated unconditionally and selected (7 packed FMAs instead of a divergent branch); the
+// near-pi form (rare) falls back to the scalar code on each half.
+GIK_HD void log6_pre(const F2 (&R)[9], Log6Mid<F2>& m) {
+  const F2 vx = R[7] - R[5], vy = R[2] - R[6], vz = R[3] - R[1];
+  const F2 tr = R[0] + R[4] + R[8];
+  const F2 c = min_(max_((tr - F2(1.0f)) * F2(0.5f), F2(-1.0f)), F2(1.0f));
+  const F2 s = F2(0.5f) * sqrt_(vx * vx + vy * vy + vz * vz);
+  const F2 theta = atan2_pos(s, c);
+  const F2 tiny = F2(Num<float>::kTinyS);
+  const F2 fac = sel_(gt_(s, tiny), F2(0.5f) * (theta * rcp_(s)), F2(0.5f));
+  m.wx = fac * vx; m.wy = fac * vy; m.wz = fac * vz;
+  const F2 t2 = theta * theta;
+  const B2 front = ge_(c, F2(0.0f));
+  const F2 num = sel_(front, F2(1.0f) + c, s);
+  const F2 den = sel_(front, s, F2(1.0f) - c);
+  const F2 alpha_g = F2(0.5f) * theta * (num * rcp_(max_(den, tiny)));
+  const F2 beta_g = (F2(1.0f) - alpha_g) * rcp_(max_(t2, tiny));
+  const F2 alpha_s = F2(1.0f) - t2 * (F2(1.0f / 12) + t2 * (F2(1.0f / 720) + t2 * F2(1.0f / 30240)));
+  const F2 beta_s = F2(1.0f / 12) + t2 * (F2(1.0f / 720) + t2 * (F2(1.0f / 30240) + t2 * F2(1.0f / 1209600)));
+  const B2 small = lt_(t2, F2(Num<float>::kSeriesT2));
+  m.alpha = sel_(small, alpha_s, alpha_g);
+  m.beta = sel_(small, beta_s, beta_g);
+  m.vx = vx; m.vy = vy; m.vz = vz; m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
+  m.c = c; m.theta = theta;
+}
+
+GIK_HD void log6_post(const Log6Mid<F2>& m, const F2 (&p)[3], F2 (&e)[6]) {
+  const float lim = 3.14159265358979323846f - 1e-2f;
+  if (m.theta.x >= lim || m.theta.y >= lim) {      // pinocchio's near-pi form on either hand: scalar code per half
+    Log6Mid<float> ml, mr;
+    ml.vx = m.vx.x; ml.vy = m.vy.x; ml.vz = m.vz.x; ml.d0 = m.d0.x; ml.d1 = m.d1.x; ml.d2 = m.d2.x; ml.c = m.c.x;
+    ml.theta = m.theta.x; ml.wx = m.wx.x; ml.wy = m.wy.x; ml.wz = m.wz.x; ml.alpha = m.alpha.x; ml.beta = m.beta.x;
+    mr.vx = m.vx.y; mr.vy = m.vy.y; mr.vz = m.vz.y; mr.d0 = m.d0.y; mr.d1 = m.d1.y; mr.d2 = m.d2.y; mr.c = m.c.y;
+    mr.theta = m.theta.y; mr.wx = m.wx.y; mr.wy = m.wy.y; mr.wz = m.wz.y; mr.alpha = m.alpha.y; mr.beta = m.beta.y;
+    const float pl[3] = {p[0].x, p[1].x, p[2].x}, pr[3] = {p[0].y, p[1].y, p[2].y};
+    float el[6], er[6];
+    log6_post(ml, pl, el);
+    log6_post(mr, pr, er);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) e[i] = F2(el[i], er[i]);
+    return;
+  }
+  const F2 wx = m.wx, wy = m.wy, wz = m.wz;
+  const F2 wp = m.beta * (wx * p[0] + wy * p[1] + wz * p[2]);
+  e[0] = m.alpha * p[0] - F2(0.5f) * (wy * p[2] - wz * p[1]) + wp * wx;
+  e[1] = m.alpha * p[1] - F2(0.5f) * (wz * p[0] - wx * p[2]) + wp * wy;
+  e[2] = m.alpha * p[2] - F2(0.5f) * (wx * p[1] - wy * p[0]) + wp * wz;
+  e[3] = wx; e[4] = wy; e[5] = wz;
+}
+
 template <typename T>
 GIK_HD void log6(const T (&R)[9], const T (&p)[3], T (&e)[6]) {
   Log6Mid<T> m;
@@ -480,9 +557,6 @@ GIK_HD void hook_target(const ArmConst<T>& ac, const T (&cube)[12], T (&tgt)[12]
 // e = log6(hand^-1 * target), hand^-1 = (B, b); in two halves (see log6_pre / log6_post)
 template <typename T>
 struct ErrMid { Log6Mid<T> m; T p[3]; };
-template <>
-struct ErrMid<F2> { Log6Mid<float> ml, mr; float pl[3], pr[3]; };
-
 template <typename T>
 GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12], ErrMid<T>& em) {
   T R[9];
@@ -497,32 +571,6 @@ GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12],
 }
 template <typename T>
 GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post(em.m, em.p, e); }
-
-// both hands at once: the products are packed, log6 (branches, transcendental functions) runs per half
-GIK_HD void hand_error_pre(const F2 (&B)[9], const F2 (&b)[3], const F2 (&tgt)[12], ErrMid<F2>& em) {
-  F2 R[9], p[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      R[3 * r + c] = B[3 * r] * tgt[c] + B[3 * r + 1] * tgt[3 + c] + B[3 * r + 2] * tgt[6 + c];
-    p[r] = b[r] + B[3 * r] * tgt[9] + B[3 * r + 1] * tgt[10] + B[3 * r + 2] * tgt[11];
-  }
-  float Rl[9], Rr[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { Rl[i] = R[i].x; Rr[i] = R[i].y; }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { em.pl[i] = p[i].x; em.pr[i] = p[i].y; }
-  log6_pre(Rl, em.ml);
-  log6_pre(Rr, em.mr);
-}
-GIK_HD void hand_error_post(const ErrMid<F2>& em, F2 (&e)[6]) {
-  float el[6], er[6];
-  log6_post(em.ml, em.pl, el);
-  log6_post(em.mr, em.pr, er);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) e[i] = F2(el[i], er[i]);
-}
 
 // One hand's share of the damped least-squares step, in two phases around the only coupling between the hands (the
 // chest joint).  With G = A A^T + lambda I = L L^T (A = 6x6 arm block, c = chest column):

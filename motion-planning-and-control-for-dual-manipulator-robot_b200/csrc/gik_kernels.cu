@@ -51,6 +51,12 @@ struct SolveArgs {
   int64_t q_sc, q_si, pose_sc, pose_si, out_sc, out_si, res_sc, res_si;
   // streamed input (host-resident batches): problems [0, *ready) are resident; a refill waits for the ones it takes
   const unsigned long long* ready;
+  // continuation launches (the keep-descending-while-colliding tail, gik_solve_success_*): work item c of the queue is
+  // column sel[c] of the arrays, *n_sel (device) items exist (n is only the upper bound the grid was sized for), and the
+  // problem resumes at iteration it0[column].  All three null for an ordinary launch.
+  const int64_t* sel;
+  const int64_t* n_sel;
+  const int32_t* it0;
   int32_t* iters;       // [n] or null (edges: iters_total)
   T* resid;             // [2][n] or null
   // edge mode
@@ -95,7 +101,8 @@ template <typename T, int MODE, uint32_t TZ, bool WRIST = false>
 __global__ void __launch_bounds__(GIK_THREADS, Launch<T>::kMinBlocks)
 gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant__ SolveArgs<T> a) {
   const int lane = threadIdx.x & 31;
-  const int64_t n = a.n;
+  const int64_t n_cols = a.n;                                                 // columns of the arrays
+  const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;          // work items of this launch
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -132,9 +139,9 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
         if (cand < n) {
-          idx = cand;
+          idx = a.sel ? a.sel[cand] : cand;
           active = true;
-          it = 0;
+          it = a.it0 ? a.it0[idx] : 0;
           r_mark = T(3.0e38);
 #pragma unroll
           for (int i = 0; i < kActive; ++i) q[i] = ld_in(a.q_init + (int64_t)tab.act_q[i] * a.q_sc + idx * a.q_si);
@@ -200,15 +207,15 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       } else {
         it_total += it;
         if (ok) {
-          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n;
+          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n_cols;
 #pragma unroll
-          for (int i = 0; i < kActive; ++i) dst[(int64_t)tab.act_q[i] * n + idx] = q[i];
+          for (int i = 0; i < kActive; ++i) dst[(int64_t)tab.act_q[i] * n_cols + idx] = q[i];
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
             T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
-            dst[(int64_t)j * n + idx] = v;
+            dst[(int64_t)j * n_cols + idx] = v;
           }
         }
         if (ok && step < nsteps) {
@@ -246,7 +253,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
 #define GIK_LANE2_INNER true   // measured against the single-loop form on 2^20 problems: 38.30 -> 36.75 ms (27.3 -> 28.5 M solves/s)
 #endif
 #ifndef GIK_MINB_LANE2_WRIST
-#define GIK_MINB_LANE2_WRIST 3   // 168 registers, no spills: 39.9 M solves/s on 2^20 problems against 39.5 M at 4 blocks (128 registers, ~270 B of spills), 34.0 M at 5, 23.6 M at 6
+#define GIK_MINB_LANE2_WRIST 4   // 128 registers (~190 B of spills outside the iteration).  2^20 problems, packed log6: 42.2 M solves/s
+                                 // against 41.2 M at 3 blocks (144 registers, none) and 38.0 M at 5 (96 registers)
 #endif
 template <int MODE, uint32_t TZ, bool WRIST = false>
 __global__ void __launch_bounds__(GIK_THREADS, (WRIST ? GIK_MINB_LANE2_WRIST : GIK_MINB_LANE2))
@@ -254,7 +262,8 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
                        const __grid_constant__ SolveArgs<float> a) {
   using T = float;
   const int lane = threadIdx.x & 31;
-  const int64_t n = a.n;
+  const int64_t n_cols = a.n;                                                 // columns of the arrays
+  const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;          // work items of this launch
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -305,9 +314,9 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
         if (cand < n) {
-          idx = cand;
+          idx = a.sel ? a.sel[cand] : cand;
           active = true;
-          it = 0;
+          it = a.it0 ? a.it0[idx] : 0;
           r_mark = T(3.0e38);
           q0 = ld_in(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
@@ -392,14 +401,14 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       } else {
         it_total += it;
         if (ok) {
-          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n;
-          store_q(dst, n, 1, idx);
+          T* dst = a.q_out + (int64_t)(step - 1) * tab.nq * n_cols;
+          store_q(dst, n_cols, 1, idx);
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
             // passive joints: clamped once any update has been applied on this edge
             T v = ld_in(a.q_init + (int64_t)j * a.q_sc + idx * a.q_si);
             if (it_total > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);
-            dst[(int64_t)j * n + idx] = v;
+            dst[(int64_t)j * n_cols + idx] = v;
           }
         }
         if (ok && step < nsteps) {
@@ -478,7 +487,8 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   const int h = lane & 1;                       // hand of this lane
   const int off = 1 + 6 * h;                    // first active-joint slot of this hand's arm
   const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
-  const int64_t n = a.n;
+  const int64_t n_cols = a.n;
+  const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;
   const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
   ArmConst<T> acr;
   T lim_lo[7], lim_hi[7];
@@ -538,9 +548,9 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (enabled && !active) {
         const int64_t cand = (int64_t)base + __popc(need & lower_pairs);
         if (cand < n) {
-          idx = cand;
+          idx = a.sel ? a.sel[cand] : cand;
           active = true;
-          it = 0;
+          it = a.it0 ? a.it0[idx] : 0;
           r_mark = T(3.0e38);
           q[0] = ld_in(a.q_init + (int64_t)tab.act_q[0] * a.q_sc + idx * a.q_si);
 #pragma unroll
@@ -631,9 +641,9 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
         const bool moved = batch ? (it > 0) : (it_total > 0);
         const int n_dst = batch ? a.n_dst : 1;
-        const int64_t ld = batch ? a.out_sc : n, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + idx : idx;
+        const int64_t ld = batch ? a.out_sc : n_cols, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + idx : idx;
         for (int d = 0; d < n_dst; ++d) {       // batch: 1 destination, or every rank's result array (fused all-gather)
-          T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n;
+          T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n_cols;
 #pragma unroll
           for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col * cs_] = q[1 + k];
           if (h == 0) {
@@ -804,7 +814,7 @@ inline bool bad_handle(gik_handle_t h) { return h == nullptr || h->magic != kMag
 inline int check_params(const gik_params_t* p) {
   if (!p) return GIK_E_NULL;
   if (!(p->eps > 0.0) || !(p->dt > 0.0) || !(p->damping >= 0.0) || p->max_iters < 0 ||
-      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP | GIK_F_CHOLESKY)) != 0 ||
+      (p->flags & ~(GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL | GIK_F_SCALAR_LANE | GIK_F_EARLY_STOP | GIK_F_CHOLESKY | GIK_F_NO_DESCEND)) != 0 ||
       (p->flags & (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL)) == (GIK_F_LANE_KERNEL | GIK_F_PAIR_KERNEL))
     return GIK_E_PARAM;
   return GIK_OK;
@@ -895,9 +905,10 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, bool wrist, int* blocks,
   return rc;
 }
 
+// force: a continuation launch that must run every problem to the iteration cap -- eps^2 = 0 can never be undercut
 template <typename T, int MODE>
-int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void* stream) {
-  a.eps2 = (T)(prm->eps * prm->eps);
+int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void* stream, bool force = false) {
+  a.eps2 = force ? T(0) : (T)(prm->eps * prm->eps);
   a.dt = (T)prm->dt;
   a.lambda = (T)prm->damping;
   a.max_iters = prm->max_iters;

@@ -59,6 +59,8 @@ def solver_for(robot, cube=None, device=None) -> GraspIK:
                          "the flattened table)")
     table = robot if isinstance(robot, KinematicTable) else from_pinocchio(robot, cube)
     s = GraspIK(table, device)
+    if not isinstance(robot, KinematicTable):
+        s._robot = robot          # its collision_model is flattened on the first collision query (GraspIK._need_scene)
     try:
         _solvers[key] = s
     except TypeError:
@@ -119,36 +121,52 @@ def computeqgrasppose(robot, qcurrent, cube, cubetarget, viz=None, *, collision=
     solver = solver_for(robot, cube)
     _setcubeplacement(robot, cube, cubetarget)
     pose = torch.from_numpy(_pose_to_array(cubetarget)).to(solver.device)
+    q0 = torch.as_tensor(np.asarray(qcurrent, dtype=np.float64).copy(), device=solver.device)
+    device_scene = False
     if collision == "auto":
         collision = _reference_collision(robot)
-        if collision is None and solver.table.meta.get("source") in ("builtin-nextage", "urdf", "pinocchio"):
-            solver._need_scene()
-            collision = lambda qq: bool(solver.collision(qq, pose)[0].item())     # GPU kernel, reference scene
-    q0 = torch.as_tensor(np.asarray(qcurrent, dtype=np.float64).copy(), device=solver.device)
+        if collision is None:
+            try:
+                solver._need_scene()
+                device_scene = True
+            except RuntimeError:
+                collision = None          # no collision model known for this robot: success = converged (documented)
 
-    q, conv, info = solver.solve(q0, pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
-                                 return_info=True)
-    q_np = q[0].double().cpu().numpy().copy()
-    success = bool(conv[0].item())
-    iters = int(info.iters[0].item())
-    resid = info.resid[0].double().cpu().numpy()
+    if device_scene:
+        # the whole predicate on the device, one call and one read-back: descent, collision test, and the reference's
+        # keep-descending-while-colliding tail (gik_solve_success_*)
+        qs, succ, _, it_d, res_d = solver.solve_success_soa(q0.to(dtype).unsqueeze(1).contiguous(),
+                                                           pose.to(dtype).unsqueeze(1).contiguous(), eps=eps, dt=dt,
+                                                           max_iters=max_iters, damping=damping)
+        q_np = qs[:, 0].double().cpu().numpy().copy()
+        success = bool(succ[0].item())
+        iters = int(it_d[0].item())
+        resid = res_d[:, 0].double().cpu().numpy()
+    else:
+        q, conv, info = solver.solve(q0, pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
+                                     return_info=True)
+        q_np = q[0].double().cpu().numpy().copy()
+        success = bool(conv[0].item())
+        iters = int(info.iters[0].item())
+        resid = info.resid[0].double().cpu().numpy()
 
-    if success and collision is not None and collision(q_np):
-        # converged but colliding: the reference keeps iterating (predicate at :70 stays False).  Re-enter the
-        # kernel one update at a time (eps below any reachable residual forces the step), testing in between.
-        success = False
-        tiny = float(np.finfo(np.float32 if dtype == torch.float32 else np.float64).tiny)
-        while iters < max_iters:
-            qd, _, inf1 = solver.solve(torch.from_numpy(q_np).to(solver.device), pose, dtype=dtype, eps=tiny, dt=dt,
-                                       max_iters=1, damping=damping, return_info=True)
-            q_np = qd[0].double().cpu().numpy().copy()
-            resid = inf1.resid[0].double().cpu().numpy()
-            iters += 1
-            if iters < max_iters and resid[0] < eps and resid[1] < eps and not collision(q_np):
-                success = True
-                break
-    if collision is not None and collision(q_np):   # inverse_geometry.py:97-98
-        success = False
+        if success and collision is not None and collision(q_np):
+            # converged but colliding under a HOST predicate (the caller's callable, or pinocchio's own computeCollisions):
+            # the reference keeps iterating (predicate at :70 stays False).  Re-enter the kernel one update at a time
+            # (eps below any reachable residual forces the step), testing in between.
+            success = False
+            tiny = float(np.finfo(np.float32 if dtype == torch.float32 else np.float64).tiny)
+            while iters < max_iters:
+                qd, _, inf1 = solver.solve(torch.from_numpy(q_np).to(solver.device), pose, dtype=dtype, eps=tiny, dt=dt,
+                                           max_iters=1, damping=damping, return_info=True)
+                q_np = qd[0].double().cpu().numpy().copy()
+                resid = inf1.resid[0].double().cpu().numpy()
+                iters += 1
+                if iters < max_iters and resid[0] < eps and resid[1] < eps and not collision(q_np):
+                    success = True
+                    break
+        if collision is not None and collision(q_np):   # inverse_geometry.py:97-98
+            success = False
 
     if viz is not None:
         try:

@@ -257,12 +257,22 @@ class GraspIK:
         return self
 
     def _need_scene(self):
-        """Attach the packaged reference scene on first use -- only for the reference's own robot; any other table
-        needs an explicit attach_scene(scene) (a silently wrong collision model is worse than an error)."""
+        """Attach a collision scene on first use.  Only two cases are automatic: the built-in Nextage table gets the
+        packaged reference scene, and a solver built from a pinocchio RobotWrapper flattens that robot's OWN
+        `collision_model` (scene_from_pinocchio: its geometries, placements and pair list, whatever they are).  Any
+        other table (a URDF, a hand-made KinematicTable) needs an explicit attach_scene(scene): a silently wrong
+        collision model is worse than an error."""
         if getattr(self, "scene", None) is None:
-            if self.table.meta.get("source") not in ("builtin-nextage", "urdf", "pinocchio"):
-                raise RuntimeError("no collision scene attached: call GraspIK.attach_scene(scene) for this robot")
-            self.attach_scene()
+            src = self.table.meta.get("source")
+            robot = getattr(self, "_robot", None)
+            if src == "builtin-nextage":
+                self.attach_scene()
+            elif robot is not None and hasattr(robot, "collision_model"):
+                from .scene import scene_from_pinocchio
+                self.attach_scene(scene_from_pinocchio(robot))
+            else:
+                raise RuntimeError("no collision scene attached: call GraspIK.attach_scene(scene) for this robot "
+                                   "(scene_from_urdf / scene_from_pinocchio build one)")
 
     def collision_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None, sel: torch.Tensor | None = None) -> torch.Tensor:
         """tools.collision(robot, q) for every column: q [nq][n], cube_pose [12][n] (None = scene's cube placement)
@@ -328,64 +338,44 @@ class GraspIK:
         return self.collision_soa(qt.t().contiguous(), cp).bool()
 
     def solve_success_soa(self, q_init, pose, *, eps=EPSILON, dt=DT, max_iters=MAX_ITERS, damping=0.0, kernel=None,
-                          descend_while_colliding=True, early_stop=False):
+                          descend_while_colliding=True, early_stop=False, return_stats=False):
         """The reference's FULL success predicate on the device: `success = converged and not collision(q)`
         (inverse_geometry.py:70, 97-98), including its behaviour on converged-but-colliding iterates -- the loop keeps
-        descending (the residual keeps shrinking) and re-tests after every update until the configuration is
-        collision-free or max_iters is reached.  One batched solve, one batched collision test, then single-update
-        re-entry rounds over the problems that are converged and colliding.  That tail is what the reference pays too
-        (one collision() per extra iteration); `descend_while_colliding=False` skips it: success is then
-        `converged and not collision(q at convergence)`, which differs from the reference only if further descent
-        would have freed the collision (and in the q returned for failed problems).
-        -> (q [nq][n], success u8 [n], converged u8 [n], iters i32 [n], resid [2][n])."""
+        descending and re-tests collision(q) after every update until an iterate is free or max_iters is reached.
+        ONE stream-ordered C call (gik_solve_success_*), no host synchronisation: the batched solve, the collision test
+        of the converged problems, a continuation launch that runs the converged-but-colliding ones to the cap, and a
+        warp-per-problem kernel that decides each of them (persistent collision, or a replay that tests the undecided
+        pairs on every iterate).  `descend_while_colliding=False` (GIK_F_NO_DESCEND) evaluates the collision term once,
+        at the configuration the descent stopped at: differs only where further descent would have freed a collision,
+        and in the q returned for failed problems.
+        -> (q [nq][n], success u8 [n], converged u8 [n], iters i32 [n], resid [2][n][, stats]); stats (device int64 [4]):
+        problems decided as persistent collisions, problems replayed, replayed iterations, replays that succeeded."""
         self._need_scene()
+        self._chk_dev(q_init, pose)
+        if q_init.dtype != pose.dtype:
+            raise TypeError("q_init and pose must share a dtype")
+        n = q_init.shape[1]
+        q = torch.empty_like(q_init)
+        succ = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        conv = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        iters = torch.empty((n,), dtype=torch.int32, device=self.device)
+        resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
+        esz = 4 if q_init.dtype == torch.float32 else 8
+        nbytes = int(self._lib.gik_solve_success_scratch_bytes(self._h, n, esz))
+        scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=self.device)
+        prm = self._params(eps, dt, max_iters, damping, kernel, early_stop)
         if not descend_while_colliding:
-            # one stream-ordered C call, no host synchronisation: solve, device-side compaction, collision on the converged
-            self._chk_dev(q_init, pose)
-            n = q_init.shape[1]
-            q = torch.empty_like(q_init)
-            succ = torch.empty((n,), dtype=torch.uint8, device=self.device)
-            conv = torch.empty((n,), dtype=torch.uint8, device=self.device)
-            iters = torch.empty((n,), dtype=torch.int32, device=self.device)
-            resid = torch.empty((2, n), dtype=q_init.dtype, device=self.device)
-            scratch = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
-            prm = self._params(eps, dt, max_iters, damping, kernel, early_stop)
-            f = getattr(self._lib, f"gik_solve_success_{_sfx(q_init.dtype)}")
-            _cabi.check(f(self._h, n, self._ptr(q_init.contiguous()), self._ptr(pose.contiguous()), ctypes.byref(prm),
-                          self._ptr(q), self._ptr(succ), self._ptr(conv), self._ptr(iters), self._ptr(resid),
-                          self._ptr(scratch), self._stream()), "gik_solve_success")
-            if n:
-                self.launches += 3
-            return q, succ, conv, iters, resid
-        q, conv, iters, resid = self.solve_soa(q_init, pose, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
-                                               kernel=kernel, early_stop=early_stop)
-        convb = conv.bool()
-        # the predicate short-circuits (inverse_geometry.py:70): collision() is only evaluated where both residuals
-        # pass, so only the converged columns are tested
-        idx = torch.nonzero(convb).flatten()
-        col = self.collision_soa(q, pose, sel=idx).bool()
-        success = convb & ~col
-        pending = torch.nonzero(convb & col & (iters < max_iters)).flatten()
-        if not descend_while_colliding:
-            pending = pending[:0]
-        tiny = float(np.finfo(np.float32 if q.dtype == torch.float32 else np.float64).tiny)
-        while pending.numel():                                  # host-visible loop: sizes shrink to zero quickly
-            qs = q[:, pending].contiguous()
-            ps = pose[:, pending].contiguous()
-            q1, _, _, r1 = self.solve_soa(qs, ps, eps=tiny, dt=dt, max_iters=1, damping=damping)    # exactly one update
-            it1 = iters[pending] + 1
-            ok = (r1[0] < eps) & (r1[1] < eps) & (it1 < max_iters)            # predicate evaluated at loop index it1
-            c1 = self.collision_soa(q1, ps).bool()
-            q[:, pending] = q1
-            iters[pending] = it1
-            resid[:, pending] = r1
-            conv[pending] = ok.to(torch.uint8)
-            good = ok & ~c1
-            success[pending] = good
-            pending = pending[~good & (it1 < max_iters)]
-        # the final test of inverse_geometry.py:97-98 re-evaluates collision(q) on the returned q: for a successful
-        # problem that is the configuration just found collision-free, for the others success is already False
-        return q, success.to(torch.uint8), conv, iters, resid
+            prm.flags |= 64                                                  # GIK_F_NO_DESCEND
+        f = getattr(self._lib, f"gik_solve_success_{_sfx(q_init.dtype)}")
+        _cabi.check(f(self._h, n, self._ptr(q_init.contiguous()), self._ptr(pose.contiguous()), ctypes.byref(prm),
+                      self._ptr(q), self._ptr(succ), self._ptr(conv), self._ptr(iters), self._ptr(resid),
+                      self._ptr(scratch), self._stream()), "gik_solve_success")
+        if n:
+            self.launches += 3 if not descend_while_colliding else 6
+        if return_stats:
+            stats = scratch[nbytes - 256 + 8:nbytes - 256 + 40].view(torch.int64).clone() if n else torch.zeros(4, dtype=torch.int64, device=self.device)
+            return q, succ, conv, iters, resid, stats
+        return q, succ, conv, iters, resid
 
     # ------------------------------------------------------------------ row-major convenience ([B, ...])
     def fk(self, q: torch.Tensor):

@@ -55,6 +55,9 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
   const T eps2 = (T)(prm->eps * prm->eps), dt = (T)prm->dt, lambda = (T)prm->damping;
   const bool generic = (prm->flags & 1) != 0;   // test hook: force the TZ = 0 instantiation
   const bool no_wrist = (prm->flags & 2) != 0;  // test hook: keep the Cholesky step where the spherical-wrist step would run
+  const bool packed = (prm->flags & 4) != 0;    // fp32 only: the packed (left, right) iteration of the fp32 lane kernel
+  PackedTable pt;
+  if constexpr (sizeof(T) == 4) build_packed_table(d, pt);
   for (int64_t i = 0; i < n; ++i) {
     T q[kActive], cube[12], tgt[2][12], dq[kActive], rL = 0, rR = 0;
     for (int a = 0; a < kActive; ++a) q[a] = q_init[(int64_t)d.act_q[a] * n + i];
@@ -66,7 +69,23 @@ static int solve_impl(const gik_table_t* tab, int64_t n, const T* q_init, const 
     for (;;) {
       // same specialisation rule as launch_solve() in csrc/gik_kernels.cu
       const bool nx = (d.tzero & kNextageTZ) == kNextageTZ && !generic;
-      if (nx && lambda == T(0) && !no_wrist) ik_iteration<T, true, kNextageTZ, true>(d, q, tgt, lambda, dq, rL, rR);
+      bool done_packed = false;
+      if constexpr (sizeof(T) == 4) {
+        if (packed) {
+          F2 q2[6], tgt2[12], dq2[6];
+          float dq0;
+          for (int k = 0; k < 6; ++k) q2[k] = F2(q[1 + k], q[7 + k]);
+          for (int c = 0; c < 12; ++c) tgt2[c] = F2(tgt[0][c], tgt[1][c]);
+          if (nx && lambda == T(0) && !no_wrist) ik_iteration_packed<kNextageTZ, true>(pt, q[0], q2, tgt2, lambda, dq0, dq2, rL, rR);
+          else if (nx) ik_iteration_packed<kNextageTZ, false>(pt, q[0], q2, tgt2, lambda, dq0, dq2, rL, rR);
+          else ik_iteration_packed<0, false>(pt, q[0], q2, tgt2, lambda, dq0, dq2, rL, rR);
+          dq[0] = dq0;
+          for (int k = 0; k < 6; ++k) { dq[1 + k] = dq2[k].x; dq[7 + k] = dq2[k].y; }
+          done_packed = true;
+        }
+      }
+      if (done_packed) {}
+      else if (nx && lambda == T(0) && !no_wrist) ik_iteration<T, true, kNextageTZ, true>(d, q, tgt, lambda, dq, rL, rR);
       else if (nx) ik_iteration<T, true, kNextageTZ>(d, q, tgt, lambda, dq, rL, rR);
       else ik_iteration<T, true, 0>(d, q, tgt, lambda, dq, rL, rR);
       ok = (rL < eps2) && (rR < eps2) && (it < prm->max_iters);

@@ -93,3 +93,43 @@ def test_to_c_roundtrip(table):
     c = table.to_c()
     assert c.nq == 15 and c.hand_joint[1] == 14
     assert abs(c.joint_p[0][2] - 1.117) < 1e-15 and c.lower[7] == -3.57792
+
+
+def _fake_collision_model(scene):
+    """Duck-typed pinocchio GeometryModel carrying the packaged reference scene (what scene_from_pinocchio reads)."""
+    gos = []
+    for g in scene.geoms:
+        if g.type == 0:
+            geo = types.SimpleNamespace(halfSide=np.array(g.size, float))
+        elif g.type == 1:
+            geo = types.SimpleNamespace(radius=float(g.size[0]))
+        else:
+            geo = types.SimpleNamespace(radius=float(g.size[0]), halfLength=float(g.size[1]))
+        gos.append(types.SimpleNamespace(name=g.name, geometry=geo, parentJoint=int(g.joint) + 1, placement=_SE3(g.R, g.p)))
+    pairs = [types.SimpleNamespace(first=int(a), second=int(b)) for a, b in scene.pairs]
+    return types.SimpleNamespace(geometryObjects=gos, collisionPairs=pairs)
+
+
+def test_scene_from_pinocchio_duck_typed(table):
+    # a solver built from a pinocchio RobotWrapper flattens THAT robot's collision model (not a packaged one)
+    import gik_b200
+    ref = gik_b200.nextage_scene()
+    names = {g.name for g in ref.geoms}
+    assert "baseLink_0" in names and "obstaclebase_0" in names
+    robot, cube = _fake_pinocchio(table)
+    robot.collision_model = _fake_collision_model(ref)
+    sc = gik_b200.scene_from_pinocchio(robot)
+    assert sc.cube == ref.cube and sc.table == ref.table and sc.obstacle == ref.obstacle
+    assert np.array_equal(sc.pairs, ref.pairs) and len(sc.geoms) == len(ref.geoms) == 48
+    for a, b in zip(sc.geoms, ref.geoms):
+        assert a.type == b.type and a.joint == b.joint and np.allclose(a.R, b.R) and np.allclose(a.p, b.p)
+        assert np.allclose(np.asarray(a.size)[:len(b.size)], b.size)
+    # the cube as hpp-fcl holds it: a mesh (unit cube x meshScale 0.1) -> the box bounding its vertices
+    V = np.array([[x, y, z] for x in (-.5, .5) for y in (-.5, .5) for z in (-.5, .5)])
+    robot.collision_model.geometryObjects[-1].geometry = types.SimpleNamespace(vertices=lambda: V)
+    robot.collision_model.geometryObjects[-1].meshScale = np.array([0.1, 0.1, 0.1])
+    sc2 = gik_b200.scene_from_pinocchio(robot)
+    assert np.allclose(sc2.geoms[-1].size, [0.05, 0.05, 0.05]) and sc2.geoms[-1].type == 0
+    # a moved obstacle is seen (the packaged scene would silently ignore it)
+    robot.collision_model.geometryObjects[ref.obstacle].placement = _SE3(np.eye(3), np.array([0.5, 0.2, 0.94]))
+    assert np.allclose(gik_b200.scene_from_pinocchio(robot).geoms[ref.obstacle].p, [0.5, 0.2, 0.94])
