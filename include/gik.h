@@ -270,6 +270,10 @@ int gik_cube_collision_f64(gik_handle_t h, int64_t n, const double* cube_pose, u
 /* Measurement helpers (bench.py). */
 /* Algorithmic FLOPs of ONE descent iteration of ONE dual-arm problem (SURVEY.md 8d breakdown). */
 size_t gik_flops_per_iter(void);
+/* FLOPs the solve kernels actually EXECUTE per descent iteration of one problem, from the executed opcode mix of the
+ * committed ncu captures (FMA = 2, MUL / ADD = 1): elem_size 4 / 8, wrist = 1 for the spherical-wrist step, 0 for the
+ * block-Cholesky step.  Reported by bench.py beside the algorithmic count (roofline.frac_executed). */
+size_t gik_flops_per_iter_executed(int elem_size, int wrist);
 /* Algorithmic bytes moved per solve (inputs + outputs), elem_size = 4 or 8. */
 size_t gik_bytes_per_solve(int elem_size);
 /* Runs a register-resident FMA chain on every SM and returns the achieved TFLOP/s (FMA = 2 FLOP) of the

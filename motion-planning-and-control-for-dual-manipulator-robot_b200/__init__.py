@@ -8,7 +8,7 @@ the CPU."""
 from .model import KinematicTable, from_pinocchio, from_urdf, nextage_table          # noqa: F401
 from .scene import CollisionScene, nextage_scene, scene_from_pinocchio, scene_from_urdf                               # noqa: F401
 from .ops import (DT, EPSILON, MAX_ITERS, GraspIK, SolveInfo, as_pose12, bytes_per_solve,  # noqa: F401
-                  default_solver, flops_per_iter, fma_peak_tflops)
+                  default_solver, flops_per_iter, flops_per_iter_executed, fma_peak_tflops)
 from .inverse_geometry import apply_collision, computeqgrasppose, computeqgrasppose_batch, solver_for  # noqa: F401
 from .path import (computepath, edge_num_steps, project_edges_batch, project_path, sample_cube_placements,  # noqa: F401
                    sample_grasp_poses_batch, se3_interpolate)

@@ -100,6 +100,8 @@ def lib() -> ctypes.CDLL:
     L.gik_solve_success_scratch_bytes.argtypes = [_P, _I64, ctypes.c_int]
     L.gik_solve_success_scratch_bytes.restype = ctypes.c_size_t
     L.gik_flops_per_iter.restype = ctypes.c_size_t
+    L.gik_flops_per_iter_executed.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.gik_flops_per_iter_executed.restype = ctypes.c_size_t
     L.gik_bytes_per_solve.argtypes = [ctypes.c_int]; L.gik_bytes_per_solve.restype = ctypes.c_size_t
     L.gik_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.gik_solve_launch_dims.argtypes = [_P, ctypes.c_int, _I64, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]
@@ -117,7 +119,7 @@ EXPORTS = [
     "gik_solve_rows_f32", "gik_solve_rows_f64", "gik_solve_scatter_f32", "gik_solve_scatter_f64", "gik_best_of_f32", "gik_best_of_f64", "gik_project_edges_f32", "gik_project_edges_f64",
     "gik_scene_attach", "gik_collision_f32", "gik_collision_f64", "gik_collision_sel_f32", "gik_collision_sel_f64", "gik_solve_success_f32", "gik_solve_success_f64", "gik_solve_success_scratch_bytes", "gik_clearance_f32", "gik_clearance_f64",
     "gik_cube_collision_f32", "gik_cube_collision_f64",
-    "gik_flops_per_iter", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",
+    "gik_flops_per_iter", "gik_flops_per_iter_executed", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",
     "gik_solve_kernel_name",
     "gik_strerror", "gik_version",
 ]

@@ -34,6 +34,7 @@ template <> struct Launch<float>  { static constexpr int kMinBlocks = GIK_MINB_F
 template <> struct Launch<double> { static constexpr int kMinBlocks = GIK_MINB_F64; };
 
 enum { MODE_BATCH = 0, MODE_EDGES = 1 };
+#define GIK_FLOPS_EXEC_F32_WRIST 1111   // see gik_flops_per_iter_executed()
 
 template <typename T>
 struct SolveArgs {
@@ -1217,6 +1218,18 @@ int gik_project_edges_f64(gik_handle_t h, int64_t n_edges, int32_t max_steps, co
 // SURVEY.md 8(d) breakdown, frozen: FK 540 + pose errors 250 + LOCAL Jacobians 588 + Gram 594 + Cholesky 650 +
 // triangular solves 288 + J^T z 155 + update/clamp 52.
 size_t gik_flops_per_iter(void) { return 540 + 250 + 588 + 594 + 650 + 288 + 155 + 52; }
+
+// FLOPs the kernels actually EXECUTE per descent iteration of one problem (FMA = 2, MUL / ADD = 1), from the executed
+// opcode mix of the committed ncu captures (profiles/): packed instructions count both halves.
+//   fp32 packed lane kernel, spherical-wrist step (profiles/r2g_solve_f32_ncu.md)
+//   fp32 packed lane kernel, block-Cholesky step  (profiles/r1m_solve_f32_ncu.md: 320.8 FFMA2 + 102.6 FMUL2 + 11.1 FADD2 + 52.3 FFMA + 56.9 FMUL + 24.0 FADD)
+//   fp64 pair kernel (two lanes per problem), wrist (profiles/r2c_solve_f64_ncu.md: 2 x (186.3 DFMA + 82.7 DMUL + 17.4 DADD))
+//   fp64 pair kernel, block-Cholesky step          (profiles/r1i_solve_f64_ncu.md: 2 x (280.3 DFMA + 96.5 DMUL + 12.8 DADD))
+size_t gik_flops_per_iter_executed(int elem_size, int wrist) {
+  if (elem_size == 4) return wrist ? GIK_FLOPS_EXEC_F32_WRIST : 1696;
+  if (elem_size == 8) return wrist ? 945 : 1340;
+  return 0;
+}
 
 // in: q_init (nq) + pose (12); out: q (nq) + flag (1 B) + iters (4 B) + resid (2).  nq = 15.
 size_t gik_bytes_per_solve(int elem_size) { return (size_t)elem_size * (15 + 12 + 15 + 2) + 1 + 4; }

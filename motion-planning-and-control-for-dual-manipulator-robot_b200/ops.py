@@ -556,5 +556,9 @@ def flops_per_iter() -> int:
     return int(_cabi.lib().gik_flops_per_iter())
 
 
+def flops_per_iter_executed(elem_size: int, wrist: bool) -> int:
+    return int(_cabi.lib().gik_flops_per_iter_executed(int(elem_size), 1 if wrist else 0))
+
+
 def bytes_per_solve(elem_size: int) -> int:
     return int(_cabi.lib().gik_bytes_per_solve(elem_size))

@@ -78,6 +78,12 @@ def solve(table_c, q_init, pose12, eps=1e-3, dt=1e-2, max_iters=1000, threads=0,
     return q, conv.astype(bool), it, res
 
 
+def set_step_method(method: int):
+    """0 = pinv through the Jacobi SVD (the restatement every parity test uses); 1 = Cholesky of the normal equations
+    (bench.py's `cpu_baseline.strong` timing only)."""
+    lib().orc_set_step_method(ctypes.c_int(int(method)))
+
+
 def interpolate(A12, B12, alpha):
     A12 = _c(A12); B12 = _c(B12); alpha = _c(alpha); n = A12.shape[0]
     out = np.empty((n, 12))

@@ -208,6 +208,48 @@ static void pinv_apply(const double* J, int m, int n, const double* e, double la
   }
 }
 
+/* STRONG CPU BASELINE step (bench.py cpu_baseline.strong only; parity tests always use pinv_apply): the same
+ * vq = J^T (J J^T + lambda I)^-1 e through a dense 12 x 12 Cholesky factorisation of the normal equations instead of an
+ * SVD -- what a performance-minded CPU implementation of the reference's step would do.  Equal to pinv(J) e wherever J
+ * has full row rank; pivots are floored.  ~15x fewer flops than the Jacobi SVD above. */
+static void normal_eq_apply(const double* J, int m, int n, const double* e, double lambda, double* vq) {
+  double G[12][12], z[12];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = (i == j) ? lambda : 0.0;
+      for (int k = 0; k < n; ++k) s += J[i * n + k] * J[j * n + k];
+      G[i][j] = s;
+    }
+  for (int j = 0; j < m; ++j) {               /* Cholesky, lower */
+    double d = G[j][j];
+    for (int k = 0; k < j; ++k) d -= G[j][k] * G[j][k];
+    d = sqrt(d > 1e-300 ? d : 1e-300);
+    G[j][j] = d;
+    for (int i = j + 1; i < m; ++i) {
+      double v = G[i][j];
+      for (int k = 0; k < j; ++k) v -= G[i][k] * G[j][k];
+      G[i][j] = v / d;
+    }
+  }
+  for (int i = 0; i < m; ++i) {               /* L y = e */
+    double v = e[i];
+    for (int k = 0; k < i; ++k) v -= G[i][k] * z[k];
+    z[i] = v / G[i][i];
+  }
+  for (int i = m - 1; i >= 0; --i) {          /* L^T z = y */
+    double v = z[i];
+    for (int k = i + 1; k < m; ++k) v -= G[k][i] * z[k];
+    z[i] = v / G[i][i];
+  }
+  for (int k = 0; k < n; ++k) {
+    double v = 0.0;
+    for (int i = 0; i < m; ++i) v += J[i * n + k] * z[i];
+    vq[k] = v;
+  }
+}
+static int g_step_method = 0; /* 0 = pinv via SVD (the restatement), 1 = normal equations (strong baseline timing) */
+void orc_set_step_method(int m) { g_step_method = m; }
+
 static void hook_targets(const orc_table_t* t, const double* pose12, se3_t* tg) {
   se3_t cube;
   memcpy(cube.R, pose12, sizeof cube.R);
@@ -238,7 +280,8 @@ static int solve_one(const orc_table_t* t, const double* q0, const double* pose1
     nR = sqrt(e[6] * e[6] + e[7] * e[7] + e[8] * e[8] + e[9] * e[9] + e[10] * e[10] + e[11] * e[11]);
     if (nL < eps && nR < eps) { success = 1; break; }
     for (int h = 0; h < 2; ++h) frame_jacobian_local(t, oMi, &hand[h], h, J + 6 * nq * h);
-    pinv_apply(J, 12, nq, e, damping, vq);
+    if (g_step_method == 1) normal_eq_apply(J, 12, nq, e, damping, vq);
+    else pinv_apply(J, 12, nq, e, damping, vq);
     for (int i = 0; i < nq; ++i) {
       double v = q[i] + vq[i] * dt;                 /* pin.integrate (:86) */
       v = v < t->lower[i] ? t->lower[i] : v;         /* projecttojointlimits (:89) */
