@@ -633,6 +633,12 @@ def run_b200(args):
         sub_run("config3_fp64_64_restarts_damped", Config3(torch, solver, 65536, 64, rank, f64), f64, steps=2)
         sub_run("config4_fp32_edges", Config4(torch, solver, 4096, 256, rank, f32), f32)
         sub_run("config4_fp64_edges", Config4(torch, solver, 4096, 256, rank, f64), f64, steps=2)
+        # the sampler's nvidia-smi polling is stopped for this one: the call enqueues ten launches back to back and a
+        # concurrent nvidia-smi query can hold the driver lock for tens of milliseconds between two of them (measured:
+        # 89 ms per call with the 100 ms poll running against 46 ms without), which a one-launch step never sees
+        if sub_sampler:
+            sub_sampler.stop()
+            sub_sampler.join(timeout=2.0)
         ent = sub_run("config2_fp32_success_predicate", SuccessPredicate(torch, solver, args.n, rank, f32), f32)
         ent["value_is"] = ("success-flagged solves/s: solve + collision(q) on the converged problems + the reference's "
                            "keep-descending-while-colliding tail, one stream-ordered call (gik_solve_success_f32)")
@@ -681,6 +687,7 @@ def run_b200(args):
         if sub_sampler:
             sub_sampler.stop()
             sub["clocks"] = sub_sampler.summary()
+            sub["clocks"]["covers"] = "the fp64 / config 3 / config 4 sub-runs (polling stopped before the success-predicate run)"
 
     if rank != 0:
         if world > 1:

@@ -203,13 +203,18 @@ __device__ __forceinline__ void place_geom(const DevScene<T>* sc, int g, const T
 //     the descent from q_c -- lanes 0 / 1 run the two hands of the pair mapping -- and tests just those pairs on every
 //     iterate, stopping at the first iterate that is converged and free: the reference's decision, iterate by iterate.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool WRIST>
-__global__ void __launch_bounds__(kCollideWarps * 32)
+// Two launches of the same code: STAGE 0 classifies every pending problem (persistent -> final outputs; otherwise the
+// problem goes on the replay list) and compiles WITHOUT the IK replay, so that it runs at the collision kernel's
+// occupancy; STAGE 1 runs over the (short) replay list, repeats the classification of its problems to rebuild their
+// undecided-pair lists, and replays the descent.
+template <typename T, bool WRIST, int STAGE>
+__global__ void __launch_bounds__(kCollideWarps * 32, (STAGE == 0 ? 4 : 2))
 gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa,
                 const uint8_t* __restrict__ pb, int n_pairs, int64_t n, const int64_t* __restrict__ sel,
                 const int64_t* __restrict__ n_sel_dev, const T* __restrict__ pose, const T* __restrict__ q_fin,
                 const T* __restrict__ resid_fin, T* q, uint8_t* success, uint8_t* conv, int32_t* iters, T* resid,
-                T eps2, T dt, T lambda, int max_iters, T safety, unsigned long long* queue, unsigned long long* stats) {
+                T eps2, T dt, T lambda, int max_iters, T safety, unsigned long long* queue, unsigned long long* stats,
+                int64_t* replay_count, int64_t* replay_sel) {
   __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
   __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
   __shared__ T s_disp[kCollideWarps][GIK_MAX_GEOMS];
@@ -299,6 +304,7 @@ gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __re
     }
     if (persistent) {
       // collides on every iterate: the loop runs to the cap, q after max_iters updates, success = False
+      // (STAGE 1 only sees problems STAGE 0 found not persistent; the branch is kept for safety)
       if (lane < nq) q[(int64_t)lane * n + i] = q_fin[(int64_t)lane * n + i];
       if (lane == 0) {
         success[i] = 0; conv[i] = 0; iters[i] = max_iters;
@@ -308,6 +314,12 @@ gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __re
       __syncwarp();
       continue;
     }
+    if constexpr (STAGE == 0) {
+      if (lane == 0) replay_sel[atomicAdd((unsigned long long*)replay_count, 1ull)] = i;
+      __syncwarp();
+      continue;
+    }
+    if constexpr (STAGE == 1) {
     // ---- replay the descent from q_c, testing the undecided pairs on every iterate
     T qh[7], tgt[12];
     {
@@ -384,6 +396,7 @@ gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __re
       }
       ++it; ++trips;
     }
+    }
   }
 }
 
@@ -441,7 +454,7 @@ int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int l
 // scratch layout of gik_solve_success_* (bytes, 256-aligned blocks): two index lists with their device-side counts, the
 // continuation's outputs (q_f, residuals, flags, iteration counts), the tail kernel's work queue and counters
 struct SuccessScratch {
-  int64_t *sel1, *sel2;        // [n + 1] each: count at [0], list from [1]
+  int64_t *sel1, *sel2, *sel3; // [n + 1] each: count at [0], list from [1] (converged | pending | to replay)
   void *q_fin, *resid_fin;     // [nq][n], [2][n] of T
   uint8_t* flag_fin;           // [n]
   int32_t* iters_fin;          // [n]
@@ -455,6 +468,7 @@ static SuccessScratch carve_scratch(void* base, int64_t n, int nq, int esz) {
   char* b = (char*)base;
   s.sel1 = (int64_t*)(b + o); o += up((size_t)(n + 1) * 8);
   s.sel2 = (int64_t*)(b + o); o += up((size_t)(n + 1) * 8);
+  s.sel3 = (int64_t*)(b + o); o += up((size_t)(n + 1) * 8);
   s.q_fin = b + o; o += up((size_t)nq * n * esz);
   s.resid_fin = b + o; o += up((size_t)2 * n * esz);
   s.flag_fin = (uint8_t*)(b + o); o += up((size_t)n);
@@ -485,6 +499,7 @@ int solve_success_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose,
   SuccessScratch sc = carve_scratch(scratch, n, nq, (int)sizeof(T));
   cudaError_t e = cudaMemsetAsync(sc.sel1, 0, sizeof(int64_t), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(sc.sel2, 0, sizeof(int64_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(sc.sel3, 0, sizeof(int64_t), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(sc.queue, 0, 8 * 8, st);
   if (e != cudaSuccess) return (int)e;
   int64_t blocks = (n + 255) / 256;
@@ -511,21 +526,26 @@ int solve_success_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose,
   gik_scene_dev* sd = h->scene;
   const uint8_t* pa = sd->pairs;
   int64_t tb = (n + gik::kCollideWarps - 1) / gik::kCollideWarps;
-  const int64_t cap = (int64_t)h->sm_count * 12;
+  const int64_t cap = (int64_t)h->sm_count * 16;
   if (tb > cap) tb = cap;
   const T safety = (T)1.5;
   const bool wrist = use_wrist<T>(h, prm);
   const T eps2 = (T)(prm->eps * prm->eps);
-  if (wrist)
-    gik::gik_tail_kernel<T, true><<<(int)tb, gik::kCollideWarps * 32, 0, st>>>(
-        table_of<T>(h), scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[0], n, sc.sel2 + 1, sc.sel2, pose, (const T*)sc.q_fin,
+  // queue[0] / queue[5]: work counters of the two stages; queue[1..4]: statistics
+  auto launch_tail = [&](auto kern, int64_t blocks_, const int64_t* list, unsigned long long* q_) {
+    kern<<<(int)blocks_, gik::kCollideWarps * 32, 0, st>>>(
+        table_of<T>(h), scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[0], n, list + 1, list, pose, (const T*)sc.q_fin,
         (const T*)sc.resid_fin, q_out, success, conv, iters, resid, eps2, (T)prm->dt, (T)prm->damping, prm->max_iters, safety,
-        sc.queue, sc.queue + 1);
-  else
-    gik::gik_tail_kernel<T, false><<<(int)tb, gik::kCollideWarps * 32, 0, st>>>(
-        table_of<T>(h), scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[0], n, sc.sel2 + 1, sc.sel2, pose, (const T*)sc.q_fin,
-        (const T*)sc.resid_fin, q_out, success, conv, iters, resid, eps2, (T)prm->dt, (T)prm->damping, prm->max_iters, safety,
-        sc.queue, sc.queue + 1);
+        q_, sc.queue + 1, sc.sel3, sc.sel3 + 1);
+  };
+  const int64_t cap2 = (int64_t)h->sm_count * 2;
+  if (wrist) {
+    launch_tail(gik::gik_tail_kernel<T, true, 0>, tb, sc.sel2, sc.queue);
+    launch_tail(gik::gik_tail_kernel<T, true, 1>, tb < cap2 ? tb : cap2, sc.sel3, sc.queue + 5);
+  } else {
+    launch_tail(gik::gik_tail_kernel<T, false, 0>, tb, sc.sel2, sc.queue);
+    launch_tail(gik::gik_tail_kernel<T, false, 1>, tb < cap2 ? tb : cap2, sc.sel3, sc.queue + 5);
+  }
   return (int)cudaGetLastError();
 }
 
