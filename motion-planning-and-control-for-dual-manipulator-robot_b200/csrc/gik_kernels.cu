@@ -44,10 +44,13 @@ struct SolveArgs {
   T* q_out;             // edges: q_path [max_steps][nq][n]   (batch mode stores through q_dst / conv_dst)
   // batch-mode destinations: 1 (the caller's q_out / converged) or, for the fused all-gather, one per rank
   // (peer-mapped pointers); a result goes to column out_off + idx of arrays with out_n columns
+  // (fused all-gather: [0] is THIS rank's own array, where the lanes store; [1 .. n_dst) are the peers' arrays, filled by
+  // coalesced chunk pushes -- scatter_push below; chunk_done[c] counts the finished problems of slab chunk c)
   T* q_dst[GIK_MAX_PEERS];
   uint8_t* conv_dst[GIK_MAX_PEERS];
   int32_t n_dst;
   int64_t out_off;
+  int32_t* chunk_done;
   // element (component c, problem i) of an array lives at ptr[c * sc + i * si]: SoA [C][n] = (n, 1), rows [n][C] = (1, C)
   int64_t q_sc, q_si, pose_sc, pose_si, out_sc, out_si, res_sc, res_si;
   // streamed input (host-resident batches): problems [0, *ready) are resident; a refill waits for the ones it takes
@@ -95,6 +98,76 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
     if (upto > (unsigned long long)a.n) upto = (unsigned long long)a.n;
     while (*(const volatile unsigned long long*)a.ready < upto) __nanosleep(200);
     __threadfence();   // acquire: the slab's rows are read only after the counter that publishes them
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused all-gather (gik_solve_scatter_*): the transfer half of "solve + all-gather in one kernel".
+// A finished problem's result is stored into this rank's OWN result arrays (q_dst[0] / conv_dst[0]); the slab is cut
+// into chunks of kChunk consecutive problems and chunk_done[c] counts the finished ones.  The lane that completes a
+// chunk makes its warp push that chunk -- nq rows of kChunk values plus kChunk flags -- into every peer's arrays with
+// coalesced 16-byte stores over NVLink (loads from L2, 512 B per warp instruction per peer) instead of the ~16
+// uncoalesced 4-byte remote stores per destination and solve that a lane-by-lane scatter costs.  Chunks complete all
+// through the launch (problems are handed out in index order), so the pushes overlap the remaining solves; one
+// cross-rank barrier follows the kernel.  Message passing: result stores, __threadfence, atomicAdd (writers);
+// final atomicAdd, __threadfence, ld.global.cg (the pushing warp).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kChunkShift = 10;
+constexpr int kChunk = 1 << kChunkShift;
+
+template <typename T>
+__device__ __forceinline__ void scatter_push(const SolveArgs<T>& a, int nq, int64_t n_items, bool fin, int64_t fin_idx,
+                                             bool counts, int lane) {
+  __threadfence();
+  __syncwarp();
+  bool last = false;
+  int64_t chunk = 0;
+  if (fin && counts) {
+    chunk = fin_idx >> kChunkShift;
+    const int64_t left = n_items - (chunk << kChunkShift);
+    last = atomicAdd(a.chunk_done + chunk, 1) + 1 == (int)(left < kChunk ? left : kChunk);
+  }
+  unsigned m = __ballot_sync(0xffffffffu, last);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const int64_t ch = __shfl_sync(0xffffffffu, chunk, src);
+    __threadfence();
+    const int64_t left = n_items - (ch << kChunkShift);
+    const int cs = (int)(left < kChunk ? left : kChunk);
+    const int64_t c0 = a.out_off + (ch << kChunkShift);
+    constexpr int PER = 16 / (int)sizeof(T);
+    bool vec = (c0 % PER) == 0 && (a.out_sc % PER) == 0 && (cs % PER) == 0;
+    bool vecb = (c0 % 16) == 0 && (cs % 16) == 0;
+    for (int d = 0; d < a.n_dst; ++d) {
+      vec = vec && ((uintptr_t)a.q_dst[d] % 16) == 0;
+      vecb = vecb && ((uintptr_t)a.conv_dst[d] % 16) == 0;
+    }
+    for (int r = 0; r < nq; ++r) {
+      const int64_t o = (int64_t)r * a.out_sc + c0;
+      if (vec) {
+        for (int k = lane; k < cs / PER; k += 32) {
+          const uint4 v = __ldcg((const uint4*)(a.q_dst[0] + o) + k);
+          for (int d = 1; d < a.n_dst; ++d) ((uint4*)(a.q_dst[d] + o))[k] = v;
+        }
+      } else {
+        for (int k = lane; k < cs; k += 32) {
+          const T v = __ldcg(a.q_dst[0] + o + k);
+          for (int d = 1; d < a.n_dst; ++d) a.q_dst[d][o + k] = v;
+        }
+      }
+    }
+    if (vecb) {
+      for (int k = lane; k < cs / 16; k += 32) {
+        const uint4 v = __ldcg((const uint4*)(a.conv_dst[0] + c0) + k);
+        for (int d = 1; d < a.n_dst; ++d) ((uint4*)(a.conv_dst[d] + c0))[k] = v;
+      }
+    } else {
+      for (int k = lane; k < cs; k += 32) {
+        const uint8_t v = __ldcg(a.conv_dst[0] + c0 + k);
+        for (int d = 1; d < a.n_dst; ++d) a.conv_dst[d][c0 + k] = v;
+      }
+    }
   }
 }
 
@@ -182,6 +255,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       r_mark = rs;
     }
     const bool done = ok || (it >= a.max_iters) || stalled;
+    bool fin = false;
+    int64_t fin_idx = 0;
 
     if (!done) {
       apply_step(tab, q, dq, a.dt);
@@ -190,8 +265,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
         const int64_t col = a.out_off + idx;
-        for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
-          T* qo = a.q_dst[d];
+        {                                       // this rank's own result arrays (peers: scatter_push)
+          T* qo = a.q_dst[0];
 #pragma unroll
           for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_sc + col * a.out_si] = q[i];
           for (int p = 0; p < tab.n_passive; ++p) {
@@ -200,11 +275,12 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
             qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
-          a.conv_dst[d][col] = ok ? 1 : 0;
+          a.conv_dst[0][col] = ok ? 1 : 0;
         }
         if (a.iters) a.iters[idx] = it;
         if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
+        fin = true; fin_idx = idx;
       } else {
         it_total += it;
         if (ok) {
@@ -237,6 +313,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         }
       }
     }
+    if (MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, fin)) scatter_push(a, tab.nq, n, fin, fin_idx, true, lane);
   }
 }
 
@@ -381,12 +458,14 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       if (!GIK_LANE2_INNER) break;
       if (__any_sync(0xffffffffu, done && active)) break;
     }
+    bool fin = false;
+    int64_t fin_idx = 0;
     if (done && active) {
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
         const int64_t col = a.out_off + idx;
-        for (int d = 0; d < a.n_dst; ++d) {     // 1 destination, or every rank's result array (fused all-gather)
-          T* qo = a.q_dst[d];
+        {                                       // this rank's own result arrays (peers: scatter_push)
+          T* qo = a.q_dst[0];
           store_q(qo, a.out_sc, a.out_si, col);
           for (int p = 0; p < tab.n_passive; ++p) {
             const int j = tab.passive_q[p];
@@ -394,11 +473,12 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
             if (it > 0) v = min_(max_(tab.qlo[j], v), tab.qhi[j]);   // clamped by the first update (:89)
             qo[(int64_t)j * a.out_sc + col * a.out_si] = v;
           }
-          a.conv_dst[d][col] = ok ? 1 : 0;
+          a.conv_dst[0][col] = ok ? 1 : 0;
         }
         if (a.iters) a.iters[idx] = it;
         if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
+        fin = true; fin_idx = idx;
       } else {
         it_total += it;
         if (ok) {
@@ -429,6 +509,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         }
       }
     }
+    if (MODE == MODE_BATCH && a.n_dst > 1) scatter_push(a, tab.nq, n, fin, fin_idx, true, lane);
   }
 }
 
@@ -636,14 +717,16 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (!INNER) break;
       if (__any_sync(0xffffffffu, done && active)) break;
     }
+    bool fin = false;
+    int64_t fin_idx = 0;
     if (done && active) {
       const bool batch = (MODE == MODE_BATCH);
       if (!batch) it_total += it;
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
         const bool moved = batch ? (it > 0) : (it_total > 0);
-        const int n_dst = batch ? a.n_dst : 1;
         const int64_t ld = batch ? a.out_sc : n_cols, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + idx : idx;
-        for (int d = 0; d < n_dst; ++d) {       // batch: 1 destination, or every rank's result array (fused all-gather)
+        {                                       // batch: this rank's own result arrays (peers: scatter_push)
+          constexpr int d = 0;
           T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n_cols;
 #pragma unroll
           for (int k = 0; k < 6; ++k) dst[(int64_t)tab.act_q[off + k] * ld + col * cs_] = q[1 + k];
@@ -663,6 +746,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
         if (h == 0 && a.iters) a.iters[idx] = it;
         if (a.resid) a.resid[(int64_t)h * a.res_sc + idx * a.res_si] = sqrt_(r);
         active = false;
+        fin = true; fin_idx = idx;
       } else if (ok && step < nsteps) {
         ++step;
         it = 0;
@@ -678,6 +762,8 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
         active = false;
       }
     }
+    // (both lanes of a pair stored their halves; the even lane counts the problem)
+    if (MODE == MODE_BATCH && a.n_dst > 1) scatter_push(a, tab.nq, n, fin, fin_idx, h == 0, lane);
   }
 }
 
@@ -1021,16 +1107,39 @@ int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const
   if (rc) return rc;
   if (n == 0) return GIK_OK;
   if (!q_init || !pose || !q_all || !conv_all) return GIK_E_NULL;
+  for (int p = 0; p < n_peers; ++p)
+    if (!q_all[p] || !conv_all[p]) return GIK_E_NULL;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  // The lanes store into ONE array -- this rank's own, i.e. the one whose memory lives on this device -- and the chunk
+  // pushes copy from it into the others.  (All on this device, as in the single-GPU test: the first one.)
+  int self = 0;
+  for (int p = 0; p < n_peers; ++p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, q_all[p]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == h->device) { self = p; break; }
+  }
+  (void)cudaGetLastError();
   SolveArgs<T> a{};
   a.q_init = q_init; a.pose = pose; a.iters = iters; a.resid = resid;
-  for (int p = 0; p < n_peers; ++p) {
-    if (!q_all[p] || !conv_all[p]) return GIK_E_NULL;
-    a.q_dst[p] = q_all[p]; a.conv_dst[p] = conv_all[p];
-  }
+  a.q_dst[0] = q_all[self]; a.conv_dst[0] = conv_all[self];
+  for (int p = 0, k = 1; p < n_peers; ++p)
+    if (p != self) { a.q_dst[k] = q_all[p]; a.conv_dst[k] = conv_all[p]; ++k; }
   a.n_dst = n_peers; a.out_off = offset;
   a.n = n;
   set_soa(a, n, n_total);
-  return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+  if (n_peers > 1) {
+    cudaError_t e = cudaMallocAsync((void**)&a.chunk_done, (size_t)n_chunks * sizeof(int32_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.chunk_done, 0, (size_t)n_chunks * sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  rc = launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+  if (a.chunk_done) {
+    cudaError_t e = cudaFreeAsync(a.chunk_done, st);
+    if (rc == GIK_OK && e != cudaSuccess) rc = (int)e;
+  }
+  return rc;
 }
 
 template <typename T>

@@ -287,25 +287,30 @@ def test_wrist_form_equals_cholesky_form(solver, table):
 
 
 def test_scatter_entry_on_one_gpu(solver):
-    # gik_solve_scatter_* with two destination arrays on the SAME device standing in for two ranks: the slab lands at
-    # its column offset in both, other columns stay untouched, values equal the plain solve
-    n, n_total, off = 1000, 2500, 700
-    P = _t(make_poses(n, 71), torch.float32).t().contiguous()
-    q0 = torch.zeros((15, n), dtype=torch.float32, device="cuda:0")
-    for kern in ("lane", "lane1", "pair"):
-        ref = solver.solve_soa(q0, P, kernel=kern)
-        qa = [torch.full((15, n_total), -7.0, device="cuda:0") for _ in range(2)]
-        ca = [torch.full((n_total,), 9, dtype=torch.uint8, device="cuda:0") for _ in range(2)]
-        iters, resid = solver.solve_scatter_soa(q0, P, [t.data_ptr() for t in qa], [t.data_ptr() for t in ca], n_total, off,
-                                                kernel=kern)
-        for d in range(2):
-            assert torch.equal(qa[d][:, off:off + n], ref[0]) and torch.equal(ca[d][off:off + n], ref[1])
-            assert (qa[d][:, :off] == -7).all() and (qa[d][:, off + n:] == -7).all()
-            assert (ca[d][:off] == 9).all() and (ca[d][off + n:] == 9).all()
-        assert torch.equal(iters, ref[2]) and torch.equal(resid, ref[3])
+    # gik_solve_scatter_* with destination arrays on the SAME device standing in for the ranks: the lanes store into the
+    # first array, finished chunks of 1024 problems are pushed into the others (16-byte stores when the slab offset and
+    # the leading dimension allow it, scalar stores otherwise).  The slab lands at its column offset in all of them,
+    # other columns stay untouched, values equal the plain solve.
+    for n, n_total, off, dtype in ((3000, 8000, 2048, torch.float32),      # aligned: vector pushes, 2 full chunks + a partial one
+                                   (3000, 7001, 701, torch.float32),       # nothing aligned: scalar pushes
+                                   (1000, 2500, 700, torch.float64),
+                                   (5, 64, 17, torch.float32)):
+        P = _t(make_poses(n, 71), dtype).t().contiguous()
+        q0 = torch.zeros((15, n), dtype=dtype, device="cuda:0")
+        for kern in (("lane", "lane1", "pair") if dtype == torch.float32 else ("lane", "pair")):
+            ref = solver.solve_soa(q0, P, kernel=kern)
+            qa = [torch.full((15, n_total), -7.0, dtype=dtype, device="cuda:0") for _ in range(3)]
+            ca = [torch.full((n_total,), 9, dtype=torch.uint8, device="cuda:0") for _ in range(3)]
+            iters, resid = solver.solve_scatter_soa(q0, P, [t.data_ptr() for t in qa], [t.data_ptr() for t in ca], n_total, off,
+                                                    kernel=kern)
+            for d in range(3):
+                assert torch.equal(qa[d][:, off:off + n], ref[0]) and torch.equal(ca[d][off:off + n], ref[1]), (n, off, kern, d)
+                assert (qa[d][:, :off] == -7).all() and (qa[d][:, off + n:] == -7).all()
+                assert (ca[d][:off] == 9).all() and (ca[d][off + n:] == 9).all()
+            assert torch.equal(iters, ref[2]) and torch.equal(resid, ref[3])
     from gik_b200 import _cabi
     with pytest.raises(_cabi.GikError):                    # slab does not fit
-        solver.solve_scatter_soa(q0, P, [qa[0].data_ptr()], [ca[0].data_ptr()], n_total, n_total - 10)
+        solver.solve_scatter_soa(q0, P, [qa[0].data_ptr()], [ca[0].data_ptr()], n_total, n_total - 2)
 
 
 def test_fused_all_gather_two_gpus():
