@@ -45,12 +45,18 @@ struct SolveArgs {
   // batch-mode destinations: 1 (the caller's q_out / converged) or, for the fused all-gather, one per rank
   // (peer-mapped pointers); a result goes to column out_off + idx of arrays with out_n columns
   // (fused all-gather: [0] is THIS rank's own array, where the lanes store; [1 .. n_dst) are the peers' arrays, filled by
-  // coalesced chunk pushes -- scatter_push below; chunk_done[c] counts the finished problems of slab chunk c)
+  // coalesced chunk pushes -- "Fused all-gather" below; marks[w] = low-water mark of compute warp w, pushed[c] = chunk c
+  // of the slab has been copied to the peers)
   T* q_dst[GIK_MAX_PEERS];
   uint8_t* conv_dst[GIK_MAX_PEERS];
   int32_t n_dst;
   int64_t out_off;
-  int32_t* chunk_done;
+  int32_t* marks;
+  int32_t n_marks;
+  int32_t push_blocks;         // leading blocks of the grid that push instead of solving
+  long long* push_ctl;         // [0] F: problems [0, F) are finished, [1] every compute warp has left, [2] next chunk to push; then statistics
+  uint8_t* pushed;
+  int32_t* warp_stats;         // measurement hook (GIK_FUSED_STATS): [2] per compute warp, or null
   // element (component c, problem i) of an array lives at ptr[c * sc + i * si]: SoA [C][n] = (n, 1), rows [n][C] = (1, C)
   int64_t q_sc, q_si, pose_sc, pose_si, out_sc, out_si, res_sc, res_si;
   // streamed input (host-resident batches): problems [0, *ready) are resident; a refill waits for the ones it takes
@@ -103,75 +109,258 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fused all-gather (gik_solve_scatter_*): the transfer half of "solve + all-gather in one kernel".
-// A finished problem's result is stored into this rank's OWN result arrays (q_dst[0] / conv_dst[0]); the slab is cut
-// into chunks of kChunk consecutive problems and chunk_done[c] counts the finished ones.  The lane that completes a
-// chunk makes its warp push that chunk -- nq rows of kChunk values plus kChunk flags -- into every peer's arrays with
-// coalesced 16-byte stores over NVLink (loads from L2, 512 B per warp instruction per peer) instead of the ~16
-// uncoalesced 4-byte remote stores per destination and solve that a lane-by-lane scatter costs.  Chunks complete all
-// through the launch (problems are handed out in index order), so the pushes overlap the remaining solves; one
-// cross-rank barrier follows the kernel.  Message passing: result stores, __threadfence, atomicAdd (writers);
-// final atomicAdd, __threadfence, ld.global.cg (the pushing warp).
-// A lane counts a problem one problem LATE -- when it finishes its next one (or leaves the kernel) -- and BEFORE it
-// stores the new result: the fence then has nothing in flight to wait for.  Counting right after the stores made every
-// finish event of a warp (~440 per launch) wait for a round trip to L2: +2.4 % on the whole kernel at 2 GPUs.
+//
+// A finished problem's result is stored into this rank's OWN result arrays (q_dst[0] / conv_dst[0]) exactly as in a
+// plain launch.  Block 0 of the grid does not solve: its warps are PUSHERS that copy finished chunks of kChunk
+// consecutive problems -- nq rows of kChunk values plus kChunk flags -- into every peer's arrays with coalesced 16-byte
+// stores over NVLink (loads from L2), all through the launch, so the transfer overlaps the remaining solves.  A small
+// tail kernel (gik_push_rest_kernel, the whole machine) copies what is left when the last problem ends -- the chunks
+// that were still in flight -- and one cross-rank barrier follows.
+//
+// How a pusher knows that a chunk is finished without the solving lanes paying for it: the queue hands problems out in
+// index order, so "every problem below F is finished" holds for F = min(queue head, smallest index still being solved).
+// Each compute warp publishes a LOW-WATER MARK -- the smallest index among its lanes' current problems, in units of
+// 2^kMarkShift problems -- into marks[warp]; a pusher takes the minimum over all marks and the queue head.  A warp
+// recomputes its mark only when one of its lanes finishes (one REDUX), publishes it only when it changed (<= n >>
+// kMarkShift times per launch) and one finish event LATE, before that event's own result stores: the release fence in
+// front of the publication then has nothing in flight to wait for.  Stale marks are low, i.e. conservative.  [The first
+// form -- every finishing lane counted its problem into a per-chunk counter with a fence + atomicAdd whose result
+// decided who pushes -- cost 5.5 % of the kernel at 2 GPUs (26.17 against 24.80 ms per 2^20 problems): the fence and
+// the round trip of the atomic stalled the whole warp ~440 times per launch.]
+// Message passing: result stores, __threadfence, st.relaxed.gpu mark (compute warps); ld.relaxed.gpu marks,
+// __threadfence, ld.global.cg results (pushers).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kChunkShift = 10;
 constexpr int kChunk = 1 << kChunkShift;
+constexpr int kMarkShift = 13;
+constexpr int kMarkDone = 0x7fffffff;
 
+__device__ __forceinline__ int ld_relaxed(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(int32_t* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// compute-warp side -------------------------------------------------------------------------------------------------
+struct MarkState { int pub = 0, pending = 0, events = 0; };
 template <typename T>
-__device__ __forceinline__ void scatter_push(const SolveArgs<T>& a, int nq, int64_t n_items, bool fin, int64_t fin_idx,
-                                             bool counts, int lane) {
+__device__ __forceinline__ int mark_slot(const SolveArgs<T>& a) {          // the leading blocks hold the pushers
+  return ((int)blockIdx.x - a.push_blocks) * (GIK_THREADS / 32) + ((int)threadIdx.x >> 5);
+}
+// a lane of this warp finished: called BEFORE the results of this event are stored
+template <typename T>
+__device__ __forceinline__ void mark_publish(const SolveArgs<T>& a, MarkState& ms, int lane) {
+  if (ms.pending != ms.pub) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_relaxed(a.marks + mark_slot(a), ms.pending);
+    ms.pub = ms.pending;
+  }
+}
+// ... and AFTER the finished lanes were retired: the mark this warp may publish at its next event
+__device__ __forceinline__ void mark_update(MarkState& ms, bool active, int64_t idx) {
+  ++ms.events;
+  const int m = __reduce_min_sync(0xffffffffu, active ? (int)(idx >> kMarkShift) : kMarkDone);
+  if (m != kMarkDone) ms.pending = m;     // no lane active: the refill brings larger indices, or the warp leaves
+}
+template <typename T>
+__device__ __forceinline__ void mark_exit(const SolveArgs<T>& a, int lane) {
   __threadfence();
   __syncwarp();
-  bool last = false;
-  int64_t chunk = 0;
-  if (fin && counts) {
-    chunk = fin_idx >> kChunkShift;
-    const int64_t left = n_items - (chunk << kChunkShift);
-    last = atomicAdd(a.chunk_done + chunk, 1) + 1 == (int)(left < kChunk ? left : kChunk);
+  if (lane == 0) st_relaxed(a.marks + mark_slot(a), kMarkDone);
+}
+template <typename T>
+__device__ __forceinline__ void mark_stats(const SolveArgs<T>& a, const MarkState& ms, int lane, unsigned long long t_start) {
+  if (a.warp_stats && lane == 0) {     // measurement hook: finish events and lifetime of this warp
+    a.warp_stats[2 * mark_slot(a)] = ms.events;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.warp_stats[2 * mark_slot(a) + 1] = (int)((t - t_start) / 1000);
   }
-  unsigned m = __ballot_sync(0xffffffffu, last);
-  while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const int64_t ch = __shfl_sync(0xffffffffu, chunk, src);
-    __threadfence();
-    const int64_t left = n_items - (ch << kChunkShift);
-    const int cs = (int)(left < kChunk ? left : kChunk);
-    const int64_t c0 = a.out_off + (ch << kChunkShift);
-    constexpr int PER = 16 / (int)sizeof(T);
-    bool vec = (c0 % PER) == 0 && (a.out_sc % PER) == 0 && (cs % PER) == 0;
-    bool vecb = (c0 % 16) == 0 && (cs % 16) == 0;
-    for (int d = 0; d < a.n_dst; ++d) {
-      vec = vec && ((uintptr_t)a.q_dst[d] % 16) == 0;
-      vecb = vecb && ((uintptr_t)a.conv_dst[d] % 16) == 0;
+}
+
+// pusher side -------------------------------------------------------------------------------------------------------
+// chunk ch of the slab: rows of this rank's own arrays -> the same place in every peer's arrays (one warp)
+template <typename T>
+__device__ __forceinline__ void push_chunk(const SolveArgs<T>& a, int nq, int64_t n_items, int64_t ch, int lane) {
+  const int64_t left = n_items - (ch << kChunkShift);
+  const int cs = (int)(left < kChunk ? left : kChunk);
+  const int64_t c0 = a.out_off + (ch << kChunkShift);
+  constexpr int PER = 16 / (int)sizeof(T);
+  bool vec = (c0 % PER) == 0 && (a.out_sc % PER) == 0 && (cs % PER) == 0;
+  bool vecb = (c0 % 16) == 0 && (cs % 16) == 0;
+  for (int d = 0; d < a.n_dst; ++d) {
+    vec = vec && ((uintptr_t)a.q_dst[d] % 16) == 0;
+    vecb = vecb && ((uintptr_t)a.conv_dst[d] % 16) == 0;
+  }
+  if (vec) {
+    // flattened (row, 16-byte word) space, eight independent loads in flight per lane
+    constexpr int U = 8;
+    const int wpr = cs / PER, total = nq * wpr;
+    for (int k0 = lane; k0 < total; k0 += 32 * U) {
+      uint4 v[U];
+      int64_t o[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < total) {
+          const int r = k / wpr, w = k - r * wpr;
+          o[u] = (int64_t)r * a.out_sc + c0 + (int64_t)w * PER;
+          v[u] = __ldcg((const uint4*)(a.q_dst[0] + o[u]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k0 + 32 * u < total)
+          for (int d = 1; d < a.n_dst; ++d) *(uint4*)(a.q_dst[d] + o[u]) = v[u];
     }
+  } else {
     for (int r = 0; r < nq; ++r) {
       const int64_t o = (int64_t)r * a.out_sc + c0;
-      if (vec) {
-        for (int k = lane; k < cs / PER; k += 32) {
-          const uint4 v = __ldcg((const uint4*)(a.q_dst[0] + o) + k);
-          for (int d = 1; d < a.n_dst; ++d) ((uint4*)(a.q_dst[d] + o))[k] = v;
-        }
-      } else {
-        for (int k = lane; k < cs; k += 32) {
-          const T v = __ldcg(a.q_dst[0] + o + k);
-          for (int d = 1; d < a.n_dst; ++d) a.q_dst[d][o + k] = v;
-        }
-      }
-    }
-    if (vecb) {
-      for (int k = lane; k < cs / 16; k += 32) {
-        const uint4 v = __ldcg((const uint4*)(a.conv_dst[0] + c0) + k);
-        for (int d = 1; d < a.n_dst; ++d) ((uint4*)(a.conv_dst[d] + c0))[k] = v;
-      }
-    } else {
       for (int k = lane; k < cs; k += 32) {
-        const uint8_t v = __ldcg(a.conv_dst[0] + c0 + k);
-        for (int d = 1; d < a.n_dst; ++d) a.conv_dst[d][c0 + k] = v;
+        const T v = __ldcg(a.q_dst[0] + o + k);
+        for (int d = 1; d < a.n_dst; ++d) a.q_dst[d][o + k] = v;
       }
     }
   }
+  if (vecb) {
+    for (int k = lane; k < cs / 16; k += 32) {
+      const uint4 v = __ldcg((const uint4*)(a.conv_dst[0] + c0) + k);
+      for (int d = 1; d < a.n_dst; ++d) ((uint4*)(a.conv_dst[d] + c0))[k] = v;
+    }
+  } else {
+    for (int k = lane; k < cs; k += 32) {
+      const uint8_t v = __ldcg(a.conv_dst[0] + c0 + k);
+      for (int d = 1; d < a.n_dst; ++d) a.conv_dst[d][c0 + k] = v;
+    }
+  }
+}
+
+// The leading push_blocks blocks of a fused launch.  Warp 0 of block 0 is the LOOKOUT: it keeps reading the queue head
+// and the marks (16-byte relaxed loads, eight in flight per lane: ~2.5 us per look at 2364 marks) and posts F --
+// "problems [0, F) are finished" -- in push_ctl[0].  The other warps take chunks in order from push_ctl[2], wait until F
+// has passed the chunk, push it and flag it.  All leave as soon as every compute warp has left (all marks kMarkDone ->
+// push_ctl[1]): whatever is not pushed by then -- the ~10^5 problems that were in flight when the queue ran dry, whose
+// chunks all complete in the last moments of the launch -- is the tail kernel's, which has the whole machine.
+// [Measured on the way here: every pusher warp looking for itself, one dependent 4-byte load after the other: 16 us per
+// look, two thirds of the pushers' time, half of the chunks pushed in-kernel.  Pushers that finish the chunks F has
+// already passed before they look at the exit flag: the kernel outlives the last solve by 4 ms at 2 destinations and
+// 19 ms at 8, because F sweeps the last 10 % of the slab at the very end.]
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int4 ld_relaxed4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_relaxed(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(long long* p, long long v) {
+  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+template <typename T>
+__device__ __noinline__ void pusher_loop(const SolveArgs<T>& a, int nq, int64_t n) {
+  const int lane = threadIdx.x & 31, warp = (int)blockIdx.x * (GIK_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t n_chunks = (n + kChunk - 1) >> kChunkShift;
+  unsigned long long t_a = 0, t_b = 0;    // measurement hook (GIK_FUSED_STATS): lookout: looking / sleeping; pushers: pushing / waiting
+  int count = 0;                          // looks / chunks pushed
+  if (warp == 0) {
+    const int n4 = a.n_marks >> 2;        // (n_marks is a multiple of 4: whole blocks)
+    for (;;) {
+      const unsigned long long t0 = now_ns();
+      unsigned long long Q = 0;
+      if (lane == 0) Q = ld_relaxed(a.queue);
+      Q = __shfl_sync(0xffffffffu, Q, 0);
+      int m = kMarkDone;
+      for (int i0 = lane; i0 < n4; i0 += 32 * 8) {
+        int4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (i0 + 32 * u < n4) ? ld_relaxed4(a.marks + 4 * (i0 + 32 * u)) : make_int4(kMarkDone, kMarkDone, kMarkDone, kMarkDone);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m = min(min(m, min(v[u].x, v[u].y)), min(v[u].z, v[u].w));
+      }
+      m = __reduce_min_sync(0xffffffffu, m);
+      ++count;
+      if (m == kMarkDone) {
+        if (lane == 0) st_relaxed(a.push_ctl + 1, 1ll);
+        t_a += now_ns() - t0;
+        break;
+      }
+      int64_t F = (int64_t)m << kMarkShift;
+      if ((int64_t)Q < F) F = (int64_t)Q;
+      if (F > n) F = n;
+      __threadfence();                    // F is posted after the marks that cover it were read
+      if (lane == 0) st_relaxed(a.push_ctl, (long long)F);
+      const unsigned long long t1 = now_ns();
+      if (lane == 0 && (count & 255) == 1 && (count >> 8) < 60) {      // statistics: a trace of (time, F, queue head)
+        long long* tr = a.push_ctl + 32 + 3 * (count >> 8);
+        tr[0] = (long long)(t1 / 1000); tr[1] = (long long)F; tr[2] = (long long)Q;
+      }
+      t_a += t1 - t0;
+      __nanosleep(1000);
+      t_b += now_ns() - t1;
+    }
+  } else {
+    for (;;) {
+      long long c = 0;
+      if (lane == 0) c = (long long)atomicAdd((unsigned long long*)(a.push_ctl + 2), 1ull);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= n_chunks) break;
+      const int64_t end = ((int64_t)c + 1) << kChunkShift;
+      const int64_t need = end < n ? end : n;
+      const unsigned long long t0 = now_ns();
+      bool left = false;
+      for (;;) {
+        long long st[2] = {0, 0};
+        if (lane == 0) { st[1] = ld_relaxed(a.push_ctl + 1); st[0] = ld_relaxed(a.push_ctl); }
+        const long long Fs = __shfl_sync(0xffffffffu, st[0], 0);
+        left = __shfl_sync(0xffffffffu, st[1], 0) != 0;
+        if (left || Fs >= need) break;
+        __nanosleep(1000);
+      }
+      const unsigned long long t1 = now_ns();
+      t_b += t1 - t0;
+      if (left) break;                    // the solves are over: chunk c (not flagged) and the rest go to the tail kernel
+      __threadfence();                    // results are read after the F that covers them
+      push_chunk(a, nq, n, c, lane);
+      __syncwarp();
+      if (lane == 0) a.pushed[c] = 1;
+      t_a += now_ns() - t1;
+      ++count;
+    }
+  }
+  if (lane == 0 && warp < 8) {            // statistics of the first eight warps behind the control words
+    long long* o = a.push_ctl + 4 + 3 * warp;
+    o[0] = (long long)(t_a / 1000); o[1] = (long long)(t_b / 1000); o[2] = count;
+  }
+}
+
+// after the solve kernel, stream-ordered: every chunk the pushers did not get to
+template <typename T>
+__global__ void __launch_bounds__(128) gik_push_rest_kernel(const __grid_constant__ SolveArgs<T> a, int nq, int tag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_chunks = (a.n + kChunk - 1) >> kChunkShift;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n_chunks; c += warps)
+    if (!a.pushed[c]) {
+      push_chunk(a, nq, a.n, c, lane);
+      if (tag && lane == 0) a.pushed[c] = (uint8_t)tag;    // (statistics of the measurement hook only)
+    }
 }
 
 template <typename T, int MODE, uint32_t TZ, bool WRIST = false>
@@ -180,6 +369,10 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int64_t n_cols = a.n;                                                 // columns of the arrays
   const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;          // work items of this launch
+  if (MODE == MODE_BATCH && a.n_dst > 1 && (int)blockIdx.x < a.push_blocks) {   // fused all-gather: the leading blocks push, the others solve
+    pusher_loop(a, tab.nq, n);
+    return;
+  }
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -198,7 +391,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
   T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
   // edge mode state
   int step = 0, nsteps = 0, it_total = 0;
-  int64_t prev_idx = -1;    // fused all-gather: finished problem not yet counted in its chunk (scatter_push)
+  MarkState ms;             // fused all-gather: this warp's low-water mark
 
   for (;;) {
     // ---------------- refill: lanes without work pull the next problems from the global queue ----------------
@@ -260,10 +453,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     }
     const bool done = ok || (it >= a.max_iters) || stalled;
 
-    if (MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active)) {
-      scatter_push(a, tab.nq, n, done && active && prev_idx >= 0, prev_idx, true, lane);
-      if (done && active) prev_idx = -1;
-    }
+    const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
+    if (fused_event) mark_publish(a, ms, lane);
     if (!done) {
       apply_step(tab, q, dq, a.dt);
       ++it;
@@ -271,7 +462,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
         const int64_t col = a.out_off + idx;
-        {                                       // this rank's own result arrays (peers: scatter_push)
+        {                                       // this rank's own result arrays (peers: the pushers of block 0)
           T* qo = a.q_dst[0];
 #pragma unroll
           for (int i = 0; i < kActive; ++i) qo[(int64_t)tab.act_q[i] * a.out_sc + col * a.out_si] = q[i];
@@ -286,7 +477,6 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         if (a.iters) a.iters[idx] = it;
         if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
-        prev_idx = idx;
       } else {
         it_total += it;
         if (ok) {
@@ -319,8 +509,9 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         }
       }
     }
+    if (fused_event) mark_update(ms, active, idx);
   }
-  if (MODE == MODE_BATCH && a.n_dst > 1) scatter_push(a, tab.nq, n, prev_idx >= 0, prev_idx, true, lane);
+  if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
 
 
@@ -348,6 +539,12 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
   const int lane = threadIdx.x & 31;
   const int64_t n_cols = a.n;                                                 // columns of the arrays
   const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;          // work items of this launch
+  if (MODE == MODE_BATCH && a.n_dst > 1 && (int)blockIdx.x < a.push_blocks) {   // fused all-gather: the leading blocks push, the others solve
+    pusher_loop(a, tab.nq, n);
+    return;
+  }
+  unsigned long long t_start = 0;
+  if (a.warp_stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -380,7 +577,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
   T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
   // edge mode state
   int step = 0, nsteps = 0, it_total = 0;
-  int64_t prev_idx = -1;    // fused all-gather: finished problem not yet counted in its chunk (scatter_push)
+  MarkState ms;             // fused all-gather: this warp's low-water mark
 
   for (;;) {
     // ---------------- refill: lanes without work pull the next problems from the global queue ----------------
@@ -465,15 +662,13 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       if (!GIK_LANE2_INNER) break;
       if (__any_sync(0xffffffffu, done && active)) break;
     }
-    if (MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active)) {
-      scatter_push(a, tab.nq, n, done && active && prev_idx >= 0, prev_idx, true, lane);
-      if (done && active) prev_idx = -1;
-    }
+    const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
+    if (fused_event) mark_publish(a, ms, lane);
     if (done && active) {
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
         const int64_t col = a.out_off + idx;
-        {                                       // this rank's own result arrays (peers: scatter_push)
+        {                                       // this rank's own result arrays (peers: the pushers of block 0)
           T* qo = a.q_dst[0];
           store_q(qo, a.out_sc, a.out_si, col);
           for (int p = 0; p < tab.n_passive; ++p) {
@@ -487,7 +682,6 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         if (a.iters) a.iters[idx] = it;
         if (a.resid) { a.resid[idx * a.res_si] = sqrt_(rL); a.resid[a.res_sc + idx * a.res_si] = sqrt_(rR); }
         active = false;
-        prev_idx = idx;
       } else {
         it_total += it;
         if (ok) {
@@ -518,8 +712,10 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         }
       }
     }
+    if (fused_event) mark_update(ms, active, idx);
   }
-  if (MODE == MODE_BATCH && a.n_dst > 1) scatter_push(a, tab.nq, n, prev_idx >= 0, prev_idx, true, lane);
+  if (MODE == MODE_BATCH && a.n_dst > 1) mark_stats(a, ms, lane, t_start);
+  if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
 
 
@@ -580,6 +776,10 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   const unsigned lower_pairs = (1u << (lane & ~1)) - 1u;
   const int64_t n_cols = a.n;
   const int64_t n = a.n_sel ? min(a.n, (int64_t)*a.n_sel) : a.n;
+  if (MODE == MODE_BATCH && a.n_dst > 1 && (int)blockIdx.x < a.push_blocks) {   // fused all-gather: the leading blocks push, the others solve
+    pusher_loop(a, tab.nq, n);
+    return;
+  }
   const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
   ArmConst<T> acr;
   T lim_lo[7], lim_hi[7];
@@ -614,7 +814,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
   int64_t idx = -1;
   bool active = false, exhausted = false;
   int it = 0, step = 0, nsteps = 0, it_total = 0;
-  int64_t prev_idx = -1;     // fused all-gather: finished problem not yet counted in its chunk (scatter_push)
+  MarkState ms;              // fused all-gather: this warp's low-water mark
   T r_mark = T(3.0e38);      // early stop: squared residual sum at the last 64-iteration checkpoint
 
   // `refill` (warp-uniform): some lane pair finished a problem in the previous trip (or the loop is starting), so the
@@ -727,17 +927,15 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (!INNER) break;
       if (__any_sync(0xffffffffu, done && active)) break;
     }
-    if (MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active)) {   // (the even lane of a pair counts the problem)
-      scatter_push(a, tab.nq, n, done && active && prev_idx >= 0, prev_idx, h == 0, lane);
-      if (done && active) prev_idx = -1;
-    }
+    const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
+    if (fused_event) mark_publish(a, ms, lane);
     if (done && active) {
       const bool batch = (MODE == MODE_BATCH);
       if (!batch) it_total += it;
       if (batch || ok) {                        // store q: batch result, or path row of a converged edge step
         const bool moved = batch ? (it > 0) : (it_total > 0);
         const int64_t ld = batch ? a.out_sc : n_cols, cs_ = batch ? a.out_si : 1, col = batch ? a.out_off + idx : idx;
-        {                                       // batch: this rank's own result arrays (peers: scatter_push)
+        {                                       // batch: this rank's own result arrays (peers: the pushers of block 0)
           constexpr int d = 0;
           T* dst = batch ? a.q_dst[d] : a.q_out + (int64_t)(step - 1) * tab.nq * n_cols;
 #pragma unroll
@@ -758,7 +956,6 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
         if (h == 0 && a.iters) a.iters[idx] = it;
         if (a.resid) a.resid[(int64_t)h * a.res_sc + idx * a.res_si] = sqrt_(r);
         active = false;
-        prev_idx = idx;
       } else if (ok && step < nsteps) {
         ++step;
         it = 0;
@@ -774,8 +971,9 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
         active = false;
       }
     }
+    if (fused_event) mark_update(ms, active, idx);
   }
-  if (MODE == MODE_BATCH && a.n_dst > 1) scatter_push(a, tab.nq, n, prev_idx >= 0, prev_idx, h == 0, lane);
+  if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
 
 // ---------------- K1 / K2: forward kinematics and LOCAL frame Jacobians (parity entries) ----------------
@@ -929,13 +1127,14 @@ template <> const DevTable<double>& table_of<double>(gik_handle_t h) { return h-
 // 7 pairs per warp (586 warps) 40.6 ms against 69.6 ms for 2 pairs per warp (2048 warps); on a 16 Ki batch 1.34 ms at
 // 16 pairs per warp against 2.70 ms when spread over every resident warp slot.
 template <typename Kernel>
-int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* blocks, int* per_warp, int64_t* max_warps_out) {
+int grid_dims(gik_handle_t h, Kernel kernel, int64_t n, int max_per_warp, int* blocks, int* per_warp, int64_t* max_warps_out,
+              int reserve = 0) {   // reserve: resident block slots kept free (the pusher block of a fused launch)
   int occ = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, GIK_THREADS, 0);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
   const int64_t warps_per_block = GIK_THREADS / 32;
-  const int64_t max_blocks = (int64_t)h->sm_count * occ;
+  const int64_t max_blocks = (int64_t)h->sm_count * occ - reserve;
   const int64_t max_warps = max_blocks * warps_per_block;
   const int64_t target_warps = (int64_t)h->sm_count * 4;      // one warp per SM sub-partition
   int64_t Lw = (n + target_warps - 1) / target_warps;
@@ -972,15 +1171,16 @@ bool use_wrist(gik_handle_t h, const gik_params_t* prm) {
 // is worth more than the shared chest work (measured 7.0M vs 6.0M solves/s on 2^20 problems).
 // params.flags can force either (GIK_F_LANE_KERNEL / GIK_F_PAIR_KERNEL) for A/B measurements.
 template <typename T, int MODE>
-int choose_launch(gik_handle_t h, int64_t n, int flags, bool wrist, int* blocks, int* per_warp, bool* pair, bool* hoist = nullptr) {
+int choose_launch(gik_handle_t h, int64_t n, int flags, bool wrist, int* blocks, int* per_warp, bool* pair, bool* hoist = nullptr,
+                  int reserve = 0) {
   int64_t max_warps = 0;
   int rc;
   if constexpr (sizeof(T) == 4) {
-    if (flags & GIK_F_SCALAR_LANE) rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
-    else if (wrist) rc = grid_dims(h, gik_solve_lane2_kernel<MODE, kNextageTZ, true>, n, 32, blocks, per_warp, &max_warps);
-    else rc = grid_dims(h, gik_solve_lane2_kernel<MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+    if (flags & GIK_F_SCALAR_LANE) rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps, reserve);
+    else if (wrist) rc = grid_dims(h, gik_solve_lane2_kernel<MODE, kNextageTZ, true>, n, 32, blocks, per_warp, &max_warps, reserve);
+    else rc = grid_dims(h, gik_solve_lane2_kernel<MODE, 0>, n, 32, blocks, per_warp, &max_warps, reserve);
   } else {
-    rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps);
+    rc = grid_dims(h, gik_solve_kernel<T, MODE, 0>, n, 32, blocks, per_warp, &max_warps, reserve);
   }
   if (rc) return rc;
   *pair = sizeof(T) == 8 || n <= 16 * max_warps;
@@ -991,13 +1191,13 @@ int choose_launch(gik_handle_t h, int64_t n, int flags, bool wrist, int* blocks,
   if (hoist) *hoist = hz;
   if (*pair) {
     if constexpr (sizeof(T) == 8) {
-      if (wrist) rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr)
-                         : grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, false, true>, n, 16, blocks, per_warp, nullptr);
-      else rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, true>, n, 16, blocks, per_warp, nullptr)
-                   : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, false>, n, 16, blocks, per_warp, nullptr);
+      if (wrist) rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr, reserve)
+                         : grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, false, true>, n, 16, blocks, per_warp, nullptr, reserve);
+      else rc = hz ? grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, true>, n, 16, blocks, per_warp, nullptr, reserve)
+                   : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0, false>, n, 16, blocks, per_warp, nullptr, reserve);
     } else {
-      rc = wrist ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr)
-                 : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr);
+      rc = wrist ? grid_dims(h, gik_solve_pair_kernel<T, MODE, kNextageTZ, true, true>, n, 16, blocks, per_warp, nullptr, reserve)
+                 : grid_dims(h, gik_solve_pair_kernel<T, MODE, 0>, n, 16, blocks, per_warp, nullptr, reserve);
     }
   }
   return rc;
@@ -1016,8 +1216,13 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   int blocks = 0, lanes = 32;
   bool pair = false, hoist = false;
   const bool wrist = use_wrist<T>(h, prm);
-  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, wrist, &blocks, &lanes, &pair, &hoist);
+  const int pushers = (MODE == MODE_BATCH && a.n_dst > 1) ? a.push_blocks : 0;   // fused all-gather: the leading blocks push (see "Fused all-gather")
+  int rc = choose_launch<T, MODE>(h, a.n, prm->flags, wrist, &blocks, &lanes, &pair, &hoist, pushers);
   if (rc) return rc;
+  if (pushers) {
+    a.n_marks = getenv("GIK_FUSED_NOPUSH") ? 0 : blocks * (GIK_THREADS / 32);   // (experiment hook: everything left to the tail kernel)
+    blocks += pushers;
+  }
   a.lanes = lanes;
   a.queue = h->queues + (h->next_queue.fetch_add(1, std::memory_order_relaxed) % kQueueSlots);
   cudaError_t qe = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), (cudaStream_t)stream);
@@ -1139,17 +1344,84 @@ int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const
   a.n = n;
   set_soa(a, n, n_total);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_peers == 1) return launch_solve<T, MODE_BATCH>(h, a, prm, stream);
+  // scratch: marks (one per warp of the largest grid any solve kernel takes; zero = "nothing finished yet"), the pushers'
+  // control words + statistics, one flag per chunk
   const int64_t n_chunks = (n + kChunk - 1) / kChunk;
-  if (n_peers > 1) {
-    cudaError_t e = cudaMallocAsync((void**)&a.chunk_done, (size_t)n_chunks * sizeof(int32_t), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a.chunk_done, 0, (size_t)n_chunks * sizeof(int32_t), st);
-    if (e != cudaSuccess) return (int)e;
+  const int64_t n_marks = (int64_t)h->sm_count * 16 * (GIK_THREADS / 32);
+  const size_t marks_bytes = ((size_t)n_marks * sizeof(int32_t) + 255) / 256 * 256, ctl_bytes = 2048;
+  char* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&scratch, marks_bytes + ctl_bytes + (size_t)n_chunks, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(scratch, 0, marks_bytes + ctl_bytes + (size_t)n_chunks, st);
+  if (e != cudaSuccess) return (int)e;
+  a.marks = (int32_t*)scratch;
+  a.push_ctl = (long long*)(scratch + marks_bytes);
+  a.pushed = (uint8_t*)(scratch + marks_bytes + ctl_bytes);
+  if (getenv("GIK_FUSED_STATS")) a.warp_stats = a.marks + n_marks / 2;   // (second half of the marks allocation: grids here use <= 1/4 of it)
+  // pusher blocks: one (a lookout + three pushing warps) keeps pace with one or two destinations; more destinations
+  // mean more stores per chunk
+  a.push_blocks = n_peers <= 3 ? 1 : 2;
+  if (const char* env = getenv("GIK_PUSH_BLOCKS")) { const int v = atoi(env); if (v >= 1 && v <= 8) a.push_blocks = v; }
+  const bool stats = getenv("GIK_FUSED_STATS") != nullptr;     // measurement hook (synchronises the stream)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (stats) {
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], st);
   }
   rc = launch_solve<T, MODE_BATCH>(h, a, prm, stream);
-  if (a.chunk_done) {
-    cudaError_t e = cudaFreeAsync(a.chunk_done, st);
-    if (rc == GIK_OK && e != cudaSuccess) rc = (int)e;
+  if (stats) cudaEventRecord(ev[1], st);
+  if (rc == GIK_OK) {
+    gik_push_rest_kernel<T><<<h->sm_count * 4, 128, 0, st>>>(a, h->host.nq, stats ? 2 : 0);
+    rc = (int)cudaGetLastError();
   }
+  if (stats) {
+    cudaEventRecord(ev[2], st);
+    uint8_t* hp = (uint8_t*)malloc((size_t)n_chunks);
+    if (hp && cudaMemcpyAsync(hp, a.pushed, (size_t)n_chunks, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+      int64_t k = 0, r = 0;
+      for (int64_t c = 0; c < n_chunks; ++c) { k += hp[c] == 1; r += hp[c] == 2; }
+      float t_solve = 0.f, t_rest = 0.f;
+      cudaEventElapsedTime(&t_solve, ev[0], ev[1]);
+      cudaEventElapsedTime(&t_rest, ev[1], ev[2]);
+      fprintf(stderr, "gik fused all-gather: %lld of %lld chunks pushed inside the solve kernel (%.3f ms incl. memset), %lld by the tail kernel (%.3f ms)\n",
+              (long long)k, (long long)n_chunks, t_solve, (long long)r, t_rest);
+      long long pw[28];
+      if (a.n_marks > 0 && cudaMemcpy(pw, a.push_ctl, sizeof(pw), cudaMemcpyDeviceToHost) == cudaSuccess)
+        for (int w = 0; w < 8 && w < a.push_blocks * (GIK_THREADS / 32); ++w)
+          fprintf(stderr, w == 0 ? "  lookout warp: %lld looks, looking %lld us, sleeping %lld us\n" : "  pusher warp: %lld chunks, pushing %lld us, waiting %lld us\n",
+                  pw[4 + 3 * w + 2], pw[4 + 3 * w], pw[4 + 3 * w + 1]);
+      if (a.warp_stats && a.n_marks > 0 && 2 * a.n_marks <= n_marks / 2) {
+        int32_t* ws = (int32_t*)malloc(sizeof(int32_t) * 2 * a.n_marks);
+        if (ws && cudaMemcpy(ws, a.warp_stats, sizeof(int32_t) * 2 * a.n_marks, cudaMemcpyDeviceToHost) == cudaSuccess) {
+          int lo = 1 << 30, hi = 0, hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          long long sum = 0;
+          for (int w = 0; w < a.n_marks; ++w) { const int v = ws[2 * w]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; sum += v; }
+          for (int w = 0; w < a.n_marks; ++w) ++hist[hi > lo ? (int)((long long)(ws[2 * w] - lo) * 7 / (hi - lo)) : 0];
+          fprintf(stderr, "  finish events per compute warp: min %d, mean %.1f, max %d; histogram over [min, max] in 8 bins:", lo, (double)sum / a.n_marks, hi);
+          for (int b = 0; b < 8; ++b) fprintf(stderr, " %d", hist[b]);
+          fprintf(stderr, "\n  by sub-partition slot (warp index in block), mean events:");
+          for (int k = 0; k < GIK_THREADS / 32; ++k) {
+            long long sk = 0; int nk = 0;
+            for (int w = k; w < a.n_marks; w += GIK_THREADS / 32) { sk += ws[2 * w]; ++nk; }
+            fprintf(stderr, " %.1f", nk ? (double)sk / nk : 0.0);
+          }
+          fprintf(stderr, "\n  first 16 warps (events):");
+          for (int w = 0; w < 16 && w < a.n_marks; ++w) fprintf(stderr, " %d", ws[2 * w]);
+          fprintf(stderr, "\n");
+        }
+        free(ws);
+      }
+      long long tr[180];
+      if (a.n_marks > 0 && getenv("GIK_FUSED_TRACE") && cudaMemcpy(tr, a.push_ctl + 32, sizeof(tr), cudaMemcpyDeviceToHost) == cudaSuccess)
+        for (int k = 0; k < 60 && tr[3 * k]; ++k)
+          fprintf(stderr, "  t %lld us: F %lld, queue head %lld\n", tr[3 * k] - tr[0], tr[3 * k + 1], tr[3 * k + 2]);
+    }
+    free(hp);
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
+  e = cudaFreeAsync(scratch, st);
+  if (rc == GIK_OK && e != cudaSuccess) rc = (int)e;
   return rc;
 }
 

@@ -190,7 +190,8 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
     allocated and owned by the caller; `out=(q, converged_u8[, iters, resid])` (pinned CPU tensors) makes the host path
     allocation-free by storing into the caller's buffers instead.  With restarts=R > 1, restart 0 starts from q_init and restarts
     1..R-1 from configurations drawn uniformly inside the joint limits; the best converged candidate (smallest
-    max residual, ties -> lowest restart) is returned (BASELINE config 3).  `collision=True` makes the returned flag
+    max residual, ties -> lowest restart) is returned (BASELINE config 3; with `collision` the selection runs over the
+    candidates whose full predicate holds).  `collision=True` makes the returned flag
     the reference's full `success` (converged and collision-free on the attached scene, with the reference's
     keep-descending-while-colliding behaviour: GraspIK.solve_success_soa); `collision="once"` evaluates the collision
     term once at the configuration the descent stopped at (one sync-free call, gik_solve_success_*: same decisions
@@ -220,8 +221,6 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
             info.converged = conv.bool()
             res = res + (info,)
         return res
-    if collision:
-        raise NotImplementedError("collision=True with restarts > 1: filter the candidates with GraspIK.collision_soa")
     if restarts <= 1:
         return solver.solve(q_init, cube_pose, dtype=dtype, eps=eps, dt=dt, max_iters=max_iters, damping=damping,
                             return_info=return_info)
@@ -238,7 +237,13 @@ def computeqgrasppose_batch(robot, q_init, cube_pose, *, dtype=torch.float32, ep
     # column index p * R + r, SoA
     q_soa = cand.reshape(B * restarts, solver.nq).t().contiguous()
     pose_soa = p12.unsqueeze(1).expand(B, restarts, 12).reshape(B * restarts, 12).t().contiguous()
-    q, conv, iters, resid = solver.solve_soa(q_soa, pose_soa, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
+    if collision:
+        # every candidate gets the full predicate (collision term + keep-descending tail on the device); the selection
+        # then runs over the SUCCESSFUL candidates, so a colliding restart never shadows a free one
+        q, conv, _, iters, resid = solver.solve_success_soa(q_soa, pose_soa, eps=eps, dt=dt, max_iters=max_iters,
+                                                           damping=damping, descend_while_colliding=(collision != "once"))
+    else:
+        q, conv, iters, resid = solver.solve_soa(q_soa, pose_soa, eps=eps, dt=dt, max_iters=max_iters, damping=damping)
     qb, cb, wh = solver.best_of_soa(q, conv, resid, B, restarts)
     res = (qb.t(), cb.bool())
     if return_info:
