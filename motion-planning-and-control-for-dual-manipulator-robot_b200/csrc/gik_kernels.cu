@@ -54,7 +54,10 @@ struct SolveArgs {
   int32_t* marks;
   int32_t n_marks;
   int32_t push_blocks;         // leading blocks of the grid that push instead of solving
-  long long* push_ctl;         // [0] F: problems [0, F) are finished, [1] every compute warp has left, [2] next chunk to push; then statistics
+  int32_t top_from;            // fused launches: warps in hardware slot top_from or higher take their problems from the TOP of the
+                               // slab (0: single-ended queue)
+  long long* push_ctl;         // [0] F: problems [0, F) are finished, [1] every compute warp has left, [2] next chunk to push,
+                               // [3] compute warps that have left; then statistics
   uint8_t* pushed;
   int32_t* warp_stats;         // measurement hook (GIK_FUSED_STATS): [2] per compute warp, or null
   // element (component c, problem i) of an array lives at ptr[c * sc + i * si]: SoA [C][n] = (n, 1), rows [n][C] = (1, C)
@@ -107,6 +110,36 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
   }
 }
 
+// One refill of a warp: `need` = lanes (lane kernels) or even lanes of the pairs (pair kernel) without work, `rank` = this
+// lane's position among them.  Returns the work item of this lane, or -1 when the queue has no more.
+// Plain launches: the queue word counts the items handed out, in index order.
+// Fused all-gather launches (a.top_from > 0): the word is TWO counters -- low half: items handed out from the bottom of
+// the slab, high half: items handed out from the top -- and the warps in the high hardware slots (from_top) work downwards from
+// the top.  Why: the SM's warp scheduler serves the co-resident warps of a sub-partition in strict launch order
+// (measured with GIK_FUSED_STATS: of four co-resident warps the first finishes ~790 problems per launch, the others ~430 /
+// ~190 / ~60), so a problem on a late warp lives up to 13x longer than one on an early warp and would hold the finished
+// PREFIX -- all the pushers can ship -- back by a third of the launch.  With the late warps (17 % of the throughput)
+// working at the other end, the prefix trails the queue by the early warps' problem duration only.  The two ends meet
+// wherever they meet: no tuning, no imbalance.  A problem's arithmetic does not depend on who solves it or when.
+template <typename T>
+__device__ __forceinline__ int64_t queue_take(const SolveArgs<T>& a, int64_t n, unsigned need, int lane, int rank,
+                                              bool from_top, bool& exhausted) {
+  const int k = __popc(need), leader = __ffs(need) - 1;
+  unsigned long long old = 0;
+  if (lane == leader) old = atomicAdd(a.queue, from_top ? ((unsigned long long)k << 32) : (unsigned long long)k);
+  old = __shfl_sync(0xffffffffu, old, leader);
+  if (a.top_from == 0) {
+    if (old + k >= (unsigned long long)n) exhausted = true;
+    wait_resident(a, old + k);
+    const int64_t cand = (int64_t)old + rank;
+    return cand < n ? cand : -1;
+  }
+  const int64_t b = (int64_t)(old & 0xffffffffull), t = (int64_t)(old >> 32);
+  if (b + t + k >= n) exhausted = true;
+  const int64_t cand = from_top ? n - 1 - t - rank : b + rank;
+  return (from_top ? cand >= b : cand < n - t) ? cand : -1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fused all-gather (gik_solve_scatter_*): the transfer half of "solve + all-gather in one kernel".
 //
@@ -149,6 +182,15 @@ __device__ __forceinline__ void st_relaxed(int32_t* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Hardware slot of this warp on its SM.  The warp scheduler serves the ready warps of a sub-partition in slot order --
+// measured with GIK_FUSED_STATS on 2^20 problems, 16 warps per SM: slots 0-3 finish 763 problems per launch each, slots 4-7
+// 441, slots 8-11 177, slots 12-15 50 -- so the slot number IS the warp's priority (see queue_take).
+__device__ __forceinline__ int warp_slot() {
+  unsigned w;
+  asm volatile("mov.u32 %0, %%warpid;" : "=r"(w));
+  return (int)w;
+}
+
 // compute-warp side -------------------------------------------------------------------------------------------------
 struct MarkState { int pub = 0, pending = 0, events = 0; };
 template <typename T>
@@ -171,19 +213,28 @@ __device__ __forceinline__ void mark_update(MarkState& ms, bool active, int64_t 
   const int m = __reduce_min_sync(0xffffffffu, active ? (int)(idx >> kMarkShift) : kMarkDone);
   if (m != kMarkDone) ms.pending = m;     // no lane active: the refill brings larger indices, or the warp leaves
 }
+// the warp leaves the kernel: its mark no longer holds anything back, and it is counted in push_ctl[3]
 template <typename T>
 __device__ __forceinline__ void mark_exit(const SolveArgs<T>& a, int lane) {
   __threadfence();
   __syncwarp();
+  if (lane == 0) {
+    st_relaxed(a.marks + mark_slot(a), kMarkDone);
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(a.push_ctl + 3) : "memory");
+  }
+}
+// a warp that takes its problems from the top of the slab (queue_take) never holds the prefix back
+template <typename T>
+__device__ __forceinline__ void mark_skip(const SolveArgs<T>& a, int lane) {
   if (lane == 0) st_relaxed(a.marks + mark_slot(a), kMarkDone);
 }
 template <typename T>
-__device__ __forceinline__ void mark_stats(const SolveArgs<T>& a, const MarkState& ms, int lane, unsigned long long t_start) {
-  if (a.warp_stats && lane == 0) {     // measurement hook: finish events and lifetime of this warp
+__device__ __forceinline__ void mark_stats(const SolveArgs<T>& a, const MarkState& ms, int lane, bool from_top) {
+  if (a.warp_stats && lane == 0) {     // measurement hook: finish events of this warp and the end of the slab it worked from
     a.warp_stats[2 * mark_slot(a)] = ms.events;
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    a.warp_stats[2 * mark_slot(a) + 1] = (int)((t - t_start) / 1000);
+    unsigned wid;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    a.warp_stats[2 * mark_slot(a) + 1] = (from_top ? 1 : 0) | ((int)wid << 8);
   }
 }
 
@@ -285,31 +336,50 @@ __device__ __noinline__ void pusher_loop(const SolveArgs<T>& a, int nq, int64_t 
       unsigned long long Q = 0;
       if (lane == 0) Q = ld_relaxed(a.queue);
       Q = __shfl_sync(0xffffffffu, Q, 0);
-      int m = kMarkDone;
+      int m = kMarkDone, arg = -1;       // (arg: the warp holding the smallest mark, for the trace of the measurement hook)
       for (int i0 = lane; i0 < n4; i0 += 32 * 8) {
         int4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           v[u] = (i0 + 32 * u < n4) ? ld_relaxed4(a.marks + 4 * (i0 + 32 * u)) : make_int4(kMarkDone, kMarkDone, kMarkDone, kMarkDone);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) m = min(min(m, min(v[u].x, v[u].y)), min(v[u].z, v[u].w));
+        for (int u = 0; u < 8; ++u) {
+          const int mu = min(min(v[u].x, v[u].y), min(v[u].z, v[u].w));
+          if (mu < m) { m = mu; arg = 4 * (i0 + 32 * u) + (v[u].x == mu ? 0 : v[u].y == mu ? 1 : v[u].z == mu ? 2 : 3); }
+        }
       }
-      m = __reduce_min_sync(0xffffffffu, m);
+      {
+        const int mw = __reduce_min_sync(0xffffffffu, m);
+        const unsigned who = __ballot_sync(0xffffffffu, m == mw);
+        arg = __shfl_sync(0xffffffffu, arg, __ffs(who) - 1);
+        m = mw;
+      }
       ++count;
-      if (m == kMarkDone) {
+      long long gone = 0;
+      if (lane == 0) gone = ld_relaxed(a.push_ctl + 3);
+      gone = __shfl_sync(0xffffffffu, gone, 0);
+      if (gone >= a.n_marks) {            // every compute warp has left
         if (lane == 0) st_relaxed(a.push_ctl + 1, 1ll);
         t_a += now_ns() - t0;
         break;
       }
-      int64_t F = (int64_t)m << kMarkShift;
-      if ((int64_t)Q < F) F = (int64_t)Q;
+      // finished prefix: below every mark and inside what the bottom end of the queue has handed out
+      int64_t F = m == kMarkDone ? n : ((int64_t)m << kMarkShift);
+      if (a.top_from > 0) {
+        const int64_t b = (int64_t)(Q & 0xffffffffull), t = (int64_t)(Q >> 32);
+        if (b < F) F = b;
+        if (n - t < F) F = n - t;
+      } else if ((int64_t)Q < F) {
+        F = (int64_t)Q;
+      }
       if (F > n) F = n;
+      if (F < 0) F = 0;
       __threadfence();                    // F is posted after the marks that cover it were read
       if (lane == 0) st_relaxed(a.push_ctl, (long long)F);
       const unsigned long long t1 = now_ns();
       if (lane == 0 && (count & 255) == 1 && (count >> 8) < 60) {      // statistics: a trace of (time, F, queue head)
         long long* tr = a.push_ctl + 32 + 3 * (count >> 8);
-        tr[0] = (long long)(t1 / 1000); tr[1] = (long long)F; tr[2] = (long long)Q;
+        tr[0] = (long long)(t1 / 1000); tr[1] = (long long)F; tr[2] = ((long long)arg << 40) | (long long)(Q & 0xffffffffull);
       }
       t_a += t1 - t0;
       __nanosleep(1000);
@@ -373,6 +443,8 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     pusher_loop(a, tab.nq, n);
     return;
   }
+  const bool from_top = MODE == MODE_BATCH && a.top_from > 0 && warp_slot() >= a.top_from;   // (see queue_take)
+  if (from_top) mark_skip(a, threadIdx.x & 31);     // works outside the prefix: nothing to hold back
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -401,15 +473,9 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     // (coalesced loads).  A problem's arithmetic does not depend on the lane it lands on: results are bit-identical.
     const unsigned need = exhausted ? 0u : __ballot_sync(0xffffffffu, enabled && !active);
     if (need) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
-      wait_resident(a, base + __popc(need));
+      const int64_t cand = queue_take(a, n, need, lane, __popc(need & ((1u << lane) - 1u)), from_top, exhausted);
       if (enabled && !active) {
-        const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
-        if (cand < n) {
+        if (cand >= 0) {
           idx = a.sel ? a.sel[cand] : cand;
           active = true;
           it = a.it0 ? a.it0[idx] : 0;
@@ -454,7 +520,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
     const bool done = ok || (it >= a.max_iters) || stalled;
 
     const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
-    if (fused_event) mark_publish(a, ms, lane);
+    if (fused_event && !from_top) mark_publish(a, ms, lane);
     if (!done) {
       apply_step(tab, q, dq, a.dt);
       ++it;
@@ -509,7 +575,7 @@ gik_solve_kernel(const __grid_constant__ DevTable<T> tab, const __grid_constant_
         }
       }
     }
-    if (fused_event) mark_update(ms, active, idx);
+    if (fused_event) mark_update(ms, active, idx);      // (from_top warps: statistics only)
   }
   if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
@@ -543,8 +609,8 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
     pusher_loop(a, tab.nq, n);
     return;
   }
-  unsigned long long t_start = 0;
-  if (a.warp_stats) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  const bool from_top = MODE == MODE_BATCH && a.top_from > 0 && warp_slot() >= a.top_from;   // (see queue_take)
+  if (from_top) mark_skip(a, threadIdx.x & 31);     // works outside the prefix: nothing to hold back
   const int L = a.lanes;
   const bool enabled = lane < L;
 
@@ -587,15 +653,9 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
     // (coalesced loads).  A problem's arithmetic does not depend on the lane it lands on: results are bit-identical.
     const unsigned need = exhausted ? 0u : __ballot_sync(0xffffffffu, enabled && !active);
     if (need) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
-      wait_resident(a, base + __popc(need));
+      const int64_t cand = queue_take(a, n, need, lane, __popc(need & ((1u << lane) - 1u)), from_top, exhausted);
       if (enabled && !active) {
-        const int64_t cand = (int64_t)base + __popc(need & ((1u << lane) - 1u));
-        if (cand < n) {
+        if (cand >= 0) {
           idx = a.sel ? a.sel[cand] : cand;
           active = true;
           it = a.it0 ? a.it0[idx] : 0;
@@ -663,7 +723,7 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
       if (__any_sync(0xffffffffu, done && active)) break;
     }
     const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
-    if (fused_event) mark_publish(a, ms, lane);
+    if (fused_event && !from_top) mark_publish(a, ms, lane);
     if (done && active) {
       // ---------------- rare path: this lane's problem ended ----------------
       if (MODE == MODE_BATCH) {
@@ -712,9 +772,9 @@ gik_solve_lane2_kernel(const __grid_constant__ DevTable<float> tab, const __grid
         }
       }
     }
-    if (fused_event) mark_update(ms, active, idx);
+    if (fused_event) mark_update(ms, active, idx);      // (from_top warps: statistics only)
   }
-  if (MODE == MODE_BATCH && a.n_dst > 1) mark_stats(a, ms, lane, t_start);
+  if (MODE == MODE_BATCH && a.n_dst > 1) mark_stats(a, ms, lane, from_top);
   if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
 
@@ -780,6 +840,8 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     pusher_loop(a, tab.nq, n);
     return;
   }
+  const bool from_top = MODE == MODE_BATCH && a.top_from > 0 && warp_slot() >= a.top_from;   // (see queue_take)
+  if (from_top) mark_skip(a, threadIdx.x & 31);     // works outside the prefix: nothing to hold back
   const bool enabled = (lane >> 1) < a.lanes;   // a.lanes = pairs per warp (1..16)
   ArmConst<T> acr;
   T lim_lo[7], lim_hi[7];
@@ -831,15 +893,9 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
     const unsigned need = ((GATED && !refill) || exhausted) ? 0u : (__ballot_sync(0xffffffffu, enabled && !active) & 0x55555555u);
     bool again = false;
     if (need) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + __popc(need) >= (unsigned long long)n) exhausted = true;
-      wait_resident(a, base + __popc(need));
+      const int64_t cand = queue_take(a, n, need, lane, __popc(need & lower_pairs), from_top, exhausted);
       if (enabled && !active) {
-        const int64_t cand = (int64_t)base + __popc(need & lower_pairs);
-        if (cand < n) {
+        if (cand >= 0) {
           idx = a.sel ? a.sel[cand] : cand;
           active = true;
           it = a.it0 ? a.it0[idx] : 0;
@@ -928,7 +984,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       if (__any_sync(0xffffffffu, done && active)) break;
     }
     const bool fused_event = MODE == MODE_BATCH && a.n_dst > 1 && __any_sync(0xffffffffu, done && active);
-    if (fused_event) mark_publish(a, ms, lane);
+    if (fused_event && !from_top) mark_publish(a, ms, lane);
     if (done && active) {
       const bool batch = (MODE == MODE_BATCH);
       if (!batch) it_total += it;
@@ -971,7 +1027,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
         active = false;
       }
     }
-    if (fused_event) mark_update(ms, active, idx);
+    if (fused_event) mark_update(ms, active, idx);      // (from_top warps: statistics only)
   }
   if (MODE == MODE_BATCH && a.n_dst > 1) mark_exit(a, lane);
 }
@@ -1220,7 +1276,12 @@ int launch_solve(gik_handle_t h, SolveArgs<T>& a, const gik_params_t* prm, void*
   int rc = choose_launch<T, MODE>(h, a.n, prm->flags, wrist, &blocks, &lanes, &pair, &hoist, pushers);
   if (rc) return rc;
   if (pushers) {
-    a.n_marks = getenv("GIK_FUSED_NOPUSH") ? 0 : blocks * (GIK_THREADS / 32);   // (experiment hook: everything left to the tail kernel)
+    a.n_marks = blocks * (GIK_THREADS / 32);
+    // the warps in the upper half of the SM's occupied warp slots -- the low-priority ones -- work from the top of the slab
+    // (queue_take); needs both counters in one 64-bit word and a device-resident batch handed out by index
+    const bool two_ended = a.n < (1ll << 31) && !a.ready && !a.sel && !getenv("GIK_FUSED_ONE_ENDED");
+    const int per_sm = (blocks + pushers + h->sm_count - 1) / h->sm_count;     // blocks per SM of this launch
+    a.top_from = (two_ended && per_sm >= 2) ? (per_sm + 1) / 2 * (GIK_THREADS / 32) : 0;
     blocks += pushers;
   }
   a.lanes = lanes;
@@ -1406,6 +1467,26 @@ int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const
             for (int w = k; w < a.n_marks; w += GIK_THREADS / 32) { sk += ws[2 * w]; ++nk; }
             fprintf(stderr, " %.1f", nk ? (double)sk / nk : 0.0);
           }
+          fprintf(stderr, "\n  by launch order of the block (quarters of the compute grid), mean events:");
+          for (int qd = 0; qd < 4; ++qd) {
+            long long sk = 0; int nk = 0;
+            for (int w = a.n_marks * qd / 4; w < a.n_marks * (qd + 1) / 4; ++w) { sk += ws[2 * w]; ++nk; }
+            fprintf(stderr, " %.1f", nk ? (double)sk / nk : 0.0);
+          }
+          {
+            long long sb = 0, st2 = 0; int nb = 0, nt = 0, minb = 1 << 30;
+            for (int w = 0; w < a.n_marks; ++w) {
+              if (ws[2 * w + 1] & 1) { st2 += ws[2 * w]; ++nt; } else { sb += ws[2 * w]; ++nb; if (ws[2 * w] < minb) minb = ws[2 * w]; }
+            }
+            fprintf(stderr, "\n  warps working from the bottom: %d, mean events %.1f, min %d; from the top: %d, mean events %.1f", nb,
+                    nb ? (double)sb / nb : 0.0, nb ? minb : 0, nt, nt ? (double)st2 / nt : 0.0);
+          }
+          fprintf(stderr, "\n  by %%warpid, mean events [warps]:");
+          for (int id = 0; id < 64; ++id) {
+            long long sk = 0; int nk = 0;
+            for (int w = 0; w < a.n_marks; ++w) if ((ws[2 * w + 1] >> 8) == id) { sk += ws[2 * w]; ++nk; }
+            if (nk) fprintf(stderr, " %d:%.0f[%d]", id, (double)sk / nk, nk);
+          }
           fprintf(stderr, "\n  first 16 warps (events):");
           for (int w = 0; w < 16 && w < a.n_marks; ++w) fprintf(stderr, " %d", ws[2 * w]);
           fprintf(stderr, "\n");
@@ -1415,7 +1496,8 @@ int scatter_api(gik_handle_t h, int64_t n, const T* q_init, const T* pose, const
       long long tr[180];
       if (a.n_marks > 0 && getenv("GIK_FUSED_TRACE") && cudaMemcpy(tr, a.push_ctl + 32, sizeof(tr), cudaMemcpyDeviceToHost) == cudaSuccess)
         for (int k = 0; k < 60 && tr[3 * k]; ++k)
-          fprintf(stderr, "  t %lld us: F %lld, queue head %lld\n", tr[3 * k] - tr[0], tr[3 * k + 1], tr[3 * k + 2]);
+          fprintf(stderr, "  t %lld us: F %lld, queue head (bottom end) %lld, smallest mark held by compute warp %lld\n", tr[3 * k] - tr[0],
+                  tr[3 * k + 1], tr[3 * k + 2] & 0xffffffffffll, tr[3 * k + 2] >> 40);
     }
     free(hp);
     for (auto& x : ev) cudaEventDestroy(x);
