@@ -262,6 +262,14 @@ int gik_solve_success_f64(gik_handle_t h, int64_t n, const double* q_init, const
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, double threshold, uint8_t* clear, void* stream);
 int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube_pose, double threshold, uint8_t* clear, void* stream);
 
+/* Replaces `distanceToObstacle(robot, q)` itself (tools.py:38-51) as a value: dist [n] = the smallest distance over the
+ * pairs whose second geometry is the table or the obstacle, capped at d_max (> 0); 0 when such a pair intersects
+ * (hpp-fcl returns the negative penetration depth there -- every caller in the reference only compares the value with
+ * a positive threshold, path.py:61-62).  One launch: each pair's distance is bracketed by bisection on the margin of
+ * the same boolean GJK, to d_max / 2^20 (f32) or d_max / 2^40 (f64). */
+int gik_obstacle_distance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube_pose, double d_max, float* dist, void* stream);
+int gik_obstacle_distance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube_pose, double d_max, double* dist, void* stream);
+
 /* Replaces the cube's own collision test of path.py:51-52 / 145-146 (cube vs table, cube vs obstacle):
  * cube_pose [12][n] -> colliding [n]. */
 int gik_cube_collision_f32(gik_handle_t h, int64_t n, const float* cube_pose, uint8_t* colliding, void* stream);

@@ -107,6 +107,95 @@ gik_collision_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restri
   }
 }
 
+// distanceToObstacle(robot, q) as a VALUE (tools.py:38-51): the smallest distance over the pairs of one list, capped at
+// d_max, 0 when a pair intersects (hpp-fcl reports the negative penetration depth there; every caller in the reference
+// only compares the value with a positive threshold, path.py:61-62).  One configuration per warp like the collision
+// kernel; each lane takes pairs, and brackets ITS pair's distance by bisection on the margin of the boolean GJK ("A
+// inflated by m intersects B") inside the running minimum of the warp -- a pair whose bounding spheres are farther apart
+// than the best distance so far is skipped, a pair that does not intersect even at the best distance so far costs one
+// GJK.  `rounds` bisection steps: the value is exact to d_max / 2^rounds.
+template <typename T>
+__global__ void __launch_bounds__(kCollideWarps * 32)
+gik_distance_kernel(const DevScene<T>* __restrict__ sc, const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pb,
+                    int n_pairs, int64_t n, const T* __restrict__ q, const T* __restrict__ cube_pose, T d_max, int rounds,
+                    T* __restrict__ out) {
+  __shared__ T s_oMi[kCollideWarps][GIK_MAX_NQ][12];
+  __shared__ T s_oMg[kCollideWarps][GIK_MAX_GEOMS][12];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nq = sc->tree.nq, ng = sc->n_geoms;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    {                                               // tree FK level by level, then the geometry placements (as gik_collision_kernel)
+      T L[12];
+      int par = -1, dep = -1;
+      if (lane < nq) {
+        joint_placement(sc->tree, lane, (const T*)nullptr, __ldg(q + (int64_t)lane * n + i), L);
+        par = sc->tree.parent[lane]; dep = sc->tree.depth[lane];
+      }
+      for (int d = 0; d <= sc->tree.max_depth; ++d) {
+        if (dep == d) {
+          if (par < 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_oMi[w][lane][k] = L[k];
+          } else {
+            se3_mul12(&s_oMi[w][par][0], L, &s_oMi[w][lane][0]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int g = lane; g < ng; g += 32) {
+      const DevGeom<T>& G = sc->g[g];
+      T P[12];
+      if (g == sc->cube_geom && cube_pose) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = __ldg(cube_pose + (int64_t)k * n + i);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) P[k] = G.R[k];
+        P[9] = G.p[0]; P[10] = G.p[1]; P[11] = G.p[2];
+      }
+      if (G.joint >= 0) se3_mul12(&s_oMi[w][G.joint][0], P, &s_oMg[w][g][0]);
+      else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_oMg[w][g][k] = P[k];
+      }
+    }
+    __syncwarp();
+    T best = d_max;                                 // running minimum, warp-uniform
+    for (int k0 = 0; k0 < n_pairs && best > T(0); k0 += 32) {
+      const int k = k0 + lane;
+      T mine = best;
+      if (k < n_pairs) {
+        const int a = pa[k], b = pb[k];
+        const T* Ma = &s_oMg[w][a][0];
+        const T* Mb = &s_oMg[w][b][0];
+        const T dx = Ma[9] - Mb[9], dy = Ma[10] - Mb[10], dz = Ma[11] - Mb[11];
+        const T reach = sc->g[a].bound + sc->g[b].bound + best;
+        if (dx * dx + dy * dy + dz * dz <= reach * reach) {
+          const Shape<T> A = make_shape(sc->g[a], Ma), B = make_shape(sc->g[b], Mb);
+          if (gjk_intersect(A, B, best)) {          // closer than the best so far: bracket it
+            if (gjk_intersect(A, B, T(0))) mine = T(0);
+            else {
+              T lo = T(0), hi = best;
+              for (int r = 0; r < rounds; ++r) {
+                const T mid = T(0.5) * (lo + hi);
+                if (gjk_intersect(A, B, mid)) hi = mid; else lo = mid;
+              }
+              mine = T(0.5) * (lo + hi);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine = min_(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+      best = mine;
+    }
+    if (lane == 0) out[i] = best;
+    __syncwarp();
+  }
+}
+
 // converged problems -> index list (order irrelevant) + count, everything else gets success = 0; one atomicAdd per warp
 __global__ void __launch_bounds__(256) gik_compact_converged_kernel(int64_t n, const uint8_t* __restrict__ conv,
                                                                     uint8_t* __restrict__ success, int64_t* __restrict__ count,
@@ -449,6 +538,27 @@ int collide_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int l
   return (int)cudaGetLastError();
 }
 
+template <typename T>
+int distance_api(gik_handle_t h, int64_t n, const T* q, const T* cube_pose, int list, double d_max, T* out, void* stream) {
+  if (bad_handle(h)) return GIK_E_HANDLE;
+  if (n < 0) return GIK_E_SIZE;
+  if (!(d_max > 0.0)) return GIK_E_PARAM;
+  if (!h->scene) return GIK_E_NOSCENE;
+  if (n == 0) return GIK_OK;
+  if (!out || !q) return GIK_E_NULL;
+  DeviceGuard g(h->device);
+  if (g.err != cudaSuccess) return (int)g.err;
+  gik_scene_dev* sd = h->scene;
+  int64_t blocks = (n + gik::kCollideWarps - 1) / gik::kCollideWarps;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  const uint8_t* pa = sd->pairs + (size_t)list * 2 * GIK_MAX_PAIRS;
+  const int rounds = sizeof(T) == 4 ? 20 : 40;       // d_max / 2^rounds: below the arithmetic's own resolution
+  gik::gik_distance_kernel<T><<<(int)blocks, gik::kCollideWarps * 32, 0, (cudaStream_t)stream>>>(
+      scene_of<T>(sd), pa, pa + GIK_MAX_PAIRS, sd->n_list[list], n, q, cube_pose, (T)d_max, rounds, out);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 // scratch layout of gik_solve_success_* (bytes, 256-aligned blocks): two index lists with their device-side counts, the
@@ -618,6 +728,8 @@ size_t gik_solve_success_scratch_bytes(gik_handle_t h, int64_t n, int elem_size)
 }
 int gik_clearance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double thr, uint8_t* out, void* s) { return collide_api<float>(h, n, q, cube, 1, thr, 1, out, s); }
 int gik_clearance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double thr, uint8_t* out, void* s) { return collide_api<double>(h, n, q, cube, 1, thr, 1, out, s); }
+int gik_obstacle_distance_f32(gik_handle_t h, int64_t n, const float* q, const float* cube, double d_max, float* dist, void* s) { return distance_api<float>(h, n, q, cube, 1, d_max, dist, s); }
+int gik_obstacle_distance_f64(gik_handle_t h, int64_t n, const double* q, const double* cube, double d_max, double* dist, void* s) { return distance_api<double>(h, n, q, cube, 1, d_max, dist, s); }
 int gik_cube_collision_f32(gik_handle_t h, int64_t n, const float* cube, uint8_t* out, void* s) { return collide_api<float>(h, n, (const float*)nullptr, cube, 2, 0.0, 0, out, s); }
 int gik_cube_collision_f64(gik_handle_t h, int64_t n, const double* cube, uint8_t* out, void* s) { return collide_api<double>(h, n, (const double*)nullptr, cube, 2, 0.0, 0, out, s); }
 

@@ -69,7 +69,7 @@ def _random_endpoint(solver, a, b, sd, dtype, generator, batch=256):
 
 
 def rrt_connect_trials(robot, cubeplacementq0, cubeplacementqgoal, std_devs=STD_DEVS[:4], trials=100, *,
-                       dtype=torch.float64, generator=None, rng=None):
+                       dtype=torch.float64, generator=None, rng=None, expand=8):
     """The reference's planner experiment (path_TESTS.py:910-990): for each spread, `trials` planning queries between
     two random valid cube placements; success rate, wall time and RRT iteration statistics per spread."""
     import time
@@ -85,7 +85,7 @@ def rrt_connect_trials(robot, cubeplacementq0, cubeplacementqgoal, std_devs=STD_
             q_goal, c1 = _random_endpoint(solver, cubeplacementq0, cubeplacementqgoal, sd, dtype, generator)
             t0 = time.perf_counter()
             path, stats = computepath(q_init, q_goal, c0, c1, robot=solver, rng=rng, generator=generator, dtype=dtype,
-                                      return_stats=True)
+                                      expand=expand, return_stats=True)
             times.append(time.perf_counter() - t0)
             iters.append(stats["iterations"])
             wins += bool(path)

@@ -313,6 +313,21 @@ class GraspIK:
             self.launches += 1
         return out
 
+    def obstacle_distance_soa(self, q_soa: torch.Tensor, cube_pose_soa: torch.Tensor | None = None, d_max: float = 2.0) -> torch.Tensor:
+        """distanceToObstacle(robot, q) (tools.py:38-51) as a value -> dist [n] in q's dtype: smallest distance between
+        the robot (and cube) and the table / obstacle, capped at d_max, 0 on intersection (gik_obstacle_distance_*)."""
+        self._need_scene()
+        self._chk_dev(q_soa, cube_pose_soa)
+        n = q_soa.shape[1]
+        out = torch.empty((n,), dtype=q_soa.dtype, device=self.device)
+        f = getattr(self._lib, f"gik_obstacle_distance_{_sfx(q_soa.dtype)}")
+        cp = None if cube_pose_soa is None else cube_pose_soa.to(q_soa.dtype).contiguous()
+        _cabi.check(f(self._h, n, self._ptr(q_soa.contiguous()), self._ptr(cp), float(d_max), self._ptr(out),
+                      self._stream()), "gik_obstacle_distance")
+        if n:
+            self.launches += 1
+        return out
+
     def cube_collision_soa(self, cube_pose_soa: torch.Tensor) -> torch.Tensor:
         """The cube's own collision test (cube vs table / obstacle, path.py:51-52): cube_pose [12][n] -> u8 [n]."""
         self._need_scene()

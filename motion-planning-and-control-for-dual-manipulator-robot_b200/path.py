@@ -3,10 +3,20 @@
   * `sample_cube_placement` (path.py:27-67): uniform placement in a box, IK from `robot.q0`   -> `sample_grasp_poses_batch`
   * `project_path`         (path.py:125-163): warm-started IK along an interpolated cube edge -> `project_edges_batch`
 
-plus `project_path`, a drop-in with the reference's signature and return value for ONE edge.  The planner's tree
-logic (RRT-connect, KD-tree, path.py:186-278) is out of scope; it would call these two.  The cube-vs-scene
-collision test (path.py:51-54, 144-149) and the obstacle-distance filter (path.py:61-62) are host-side hooks the
-caller may pass in; the IK itself runs in the CUDA kernels."""
+plus `project_path`, a drop-in with the reference's signature and return value for ONE edge, and `computepath`, the
+RRT-connect driver (path.py:186-278) with the reference's tree logic on the host and its two IK call sites batched:
+samples come from a pool validated `sample_batch` at a time, and `expand` tree extensions per iteration go through ONE
+launch of the edge kernel.  The cube-vs-scene collision test (path.py:51-54, 144-149), the robot collision term of the
+grasp predicate and the obstacle-distance filter (path.py:61-62) run in the collision kernels on the attached scene
+("scene"), or as host callables the caller passes in.
+
+Deliberate differences from the reference loop (never unsafe: every returned vertex passed every reference test):
+  * an edge is marched to the first NON-CONVERGED step and THEN cut at the first step whose cube or robot collides.  The
+    reference tests the cube before the IK of each step and, for a converged-but-colliding iterate, keeps descending
+    (inverse_geometry.py:70) -- it may find a free q there and carry on with it as the next warm start, so its edges
+    can be longer than the ones returned here, never shorter;
+  * the sampler abandons stalled descents early (GIK_F_EARLY_STOP) and skips the extra descent on colliding samples:
+    accepted samples satisfy the reference's acceptance rule; which candidates are accepted can differ."""
 from __future__ import annotations
 
 import numpy as np
@@ -210,9 +220,9 @@ class _SamplePool:
         return self.q.pop(0), self.pl.pop(0)
 
 
-def _get_path(G):
-    """path.get_path (path.py:174-183)."""
-    path, node = [], G[-1]
+def _get_path(G, node=-1):
+    """path.get_path (path.py:174-183), from any vertex of the tree (the reference always starts at the last one)."""
+    path, node = [], G[node]
     while node[0] is not None:
         path.insert(0, node[1])
         node = G[node[0]]
@@ -220,13 +230,35 @@ def _get_path(G):
     return path
 
 
+def _project_batch(solver, q_start, cube_a, cube_b, step_size, dtype, scene):
+    """K edges of path.project_path (path.py:125-163) in ONE launch of the edge kernel + one batched pass of the two
+    collision tests.  q_start [K][nq], cube_a / cube_b [K][12] (numpy).  Returns per edge (q_seg [m+1,nq], cube_seg
+    [m+1,12]): the start vertex followed by the m valid steps, like the reference's (robot_path, cube_path)."""
+    q_start = np.asarray(q_start, float); a = np.asarray(cube_a, float); b = np.asarray(cube_b, float)
+    K = a.shape[0]
+    ns = (np.floor(np.linalg.norm(a[:, 9:] - b[:, 9:], axis=1) / step_size).astype(np.int32) + 1)   # path.py:129-130
+    S = int(ns.max())
+    q_path, nv = project_edges_batch(solver, q_start, a, b, num_steps=ns, max_steps=S, dtype=dtype, scene_tests=scene)
+    qp = q_path.double().cpu().numpy()
+    nv = nv.cpu().numpy()
+    A = torch.from_numpy(a)[:, None, :].expand(K, S, 12).reshape(-1, 12)
+    B = torch.from_numpy(b)[:, None, :].expand(K, S, 12).reshape(-1, 12)
+    alpha = (torch.arange(1, S + 1, dtype=torch.float64)[None, :] / torch.from_numpy(ns.astype(np.float64))[:, None]).clamp(max=1.0)
+    poses = se3_interpolate(A, B, alpha.reshape(-1)).reshape(K, S, 12).numpy()
+    return [(np.vstack([q_start[k][None], qp[k, :nv[k]]]), np.vstack([a[k][None], poses[k, :nv[k]]])) for k in range(K)]
+
+
 def computepath(qinit, qgoal, cubeplacementq0, cubeplacementqgoal, robot=None, cube=None, *, step_size=STEP_SIZE,
                 goal_tolerance=GOAL_TOLERANCE, max_iterations=MAX_ITERATIONS, max_retries=MAX_RETRIES, rng=None,
-                generator=None, dtype=torch.float64, sample_batch=512, scene=True, return_stats=False):
+                generator=None, dtype=torch.float64, sample_batch=512, scene=True, expand=8, return_stats=False):
     """Drop-in for path.computepath (path.py:194-278): bidirectional RRT over cube placements, each new vertex a grasp
-    configuration.  Same loop as the reference (goal bias 0.1, nearest vertex in configuration space, project_path
+    configuration.  Same rules as the reference -- goal bias 0.1, nearest vertex in configuration space, project_path
     towards the sample from the start tree and towards the goal placement from the goal tree, connect when the two new
-    configurations are closer than goal_tolerance); the IK, interpolation and collision work runs in the CUDA kernels.
+    configurations are closer than goal_tolerance -- with `expand` extensions per iteration instead of one: `expand`
+    targets are drawn, their nearest start-tree vertices are found in one vectorised query, and all `expand` edges (then
+    all `expand` goal-tree edges) are projected by ONE launch of the edge kernel each.  An edge's time is the latency of
+    its own warm-started chain, so `expand` edges cost what one costs and a query needs ~1/expand of the iterations.
+    `expand=1` is the reference loop step for step.  The first extension (lowest index) that connects ends the search.
     `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (built-in Nextage); `cube` is unused unless
     `robot` is a pinocchio wrapper.  Returns the list of configurations (empty on failure), like the reference."""
     solver = solver_for(robot, cube)
@@ -236,40 +268,49 @@ def computepath(qinit, qgoal, cubeplacementq0, cubeplacementqgoal, robot=None, c
     qinit, qgoal = np.asarray(qinit, float), np.asarray(qgoal, float)
     a12, b12 = _pose_to_array(cubeplacementq0), _pose_to_array(cubeplacementqgoal)
     pool = _SamplePool(solver, a12, b12, dtype, sample_batch, generator, scene)
-    test = "scene" if scene else None
-    stats = {"iterations": 0, "retries": 0, "edges": 0, "vertices": 0}
+    K = max(int(expand), 1)
+    stats = {"iterations": 0, "retries": 0, "edges": 0, "vertices": 0, "expand": K}
 
-    def nearest(points, target):            # KDTree.query of the reference (path.py:186-192): exact nearest neighbour
-        return int(np.argmin(((np.asarray(points) - target) ** 2).sum(axis=1)))
+    def nearest(points, targets):           # KDTree.query of the reference (path.py:186-192): exact nearest neighbours
+        P, T = np.asarray(points), np.asarray(targets)
+        return ((P[None, :, :] - T[:, None, :]) ** 2).sum(axis=2).argmin(axis=1)
+
+    def grow(G, C, near, segs):             # path.py:241-244: the segment's first vertex is re-added too
+        ends = []
+        for k, (sq, sc) in enumerate(segs):
+            for j in range(len(sq)):
+                G.append((len(G) - 1 if j > 0 else int(near[k]), sq[j]))
+                C.append(sc[j])
+            ends.append(len(G) - 1)
+        return ends
 
     for retry in range(max_retries):
         G_start, G_goal = [(None, qinit)], [(None, qgoal)]
         C_start, C_goal = [a12], [b12]
         for i in range(max_iterations):
             stats["iterations"] += 1
-            if rng.random() < GOAL_BIAS:
-                q_rand, cube_rand = qgoal, b12
-            else:
-                q_rand, p = pool.next()
-                cube_rand = np.concatenate([np.eye(3).reshape(9), p])
+            q_rand, cube_rand = [], []
+            for _ in range(K):
+                if rng.random() < GOAL_BIAS:
+                    q_rand.append(qgoal); cube_rand.append(b12)
+                else:
+                    q, p = pool.next()
+                    q_rand.append(q); cube_rand.append(np.concatenate([np.eye(3).reshape(9), p]))
             ns = nearest([g[1] for g in G_start], q_rand)
-            seg_q, seg_c = project_path(solver, None, G_start[ns][1], C_start[ns], cube_rand, step_size=step_size,
-                                        cube_collision=test, collision=test, dtype=dtype)
-            for j in range(len(seg_q)):     # the reference re-adds the segment's first vertex too (path.py:241-244)
-                G_start.append((len(G_start) - 1 if j > 0 else ns, seg_q[j]))
-                C_start.append(_pose_to_array(seg_c[j]))
-            q_new = seg_q[-1]
+            segs = _project_batch(solver, [G_start[j][1] for j in ns], [C_start[j] for j in ns], cube_rand, step_size,
+                                  dtype, scene)
+            ends_s = grow(G_start, C_start, ns, segs)
+            q_new = [sq[-1] for sq, _ in segs]
             ng = nearest([g[1] for g in G_goal], q_new)
-            seg_q2, seg_c2 = project_path(solver, None, G_goal[ng][1], C_goal[ng], b12, step_size=step_size,
-                                          cube_collision=test, collision=test, dtype=dtype)
-            for j in range(len(seg_q2)):
-                G_goal.append((len(G_goal) - 1 if j > 0 else ng, seg_q2[j]))
-                C_goal.append(_pose_to_array(seg_c2[j]))
-            stats["edges"] += 2
-            if np.linalg.norm(seg_q2[-1] - q_new) < goal_tolerance:
-                path = _get_path(G_start) + _get_path(G_goal)[::-1]
-                stats["vertices"] = len(G_start) + len(G_goal)
-                return (path, stats) if return_stats else path
+            segs2 = _project_batch(solver, [G_goal[j][1] for j in ng], [C_goal[j] for j in ng], [b12] * K, step_size,
+                                   dtype, scene)
+            ends_g = grow(G_goal, C_goal, ng, segs2)
+            stats["edges"] += 2 * K
+            for k in range(K):
+                if np.linalg.norm(segs2[k][0][-1] - q_new[k]) < goal_tolerance:
+                    path = _get_path(G_start, ends_s[k]) + _get_path(G_goal, ends_g[k])[::-1]
+                    stats["vertices"] = len(G_start) + len(G_goal)
+                    return (path, stats) if return_stats else path
         stats["retries"] += 1
     return ([], stats) if return_stats else []
 

@@ -3,7 +3,7 @@ the flattened model / scene and the CUDA kernels instead of pinocchio + hpp-fcl:
 
     jointlimitscost, jointlimitsviolated, projecttojointlimits   (tools.py:11-22)
     collision(robot, q)                                          (tools.py:25-35)   -> gik_collision_*
-    distanceToObstacle(robot, q)                                 (tools.py:38-51)   -> gik_clearance_* (bisection)
+    distanceToObstacle(robot, q)                                 (tools.py:38-51)   -> gik_obstacle_distance_*
     getcubeplacement / setcubeplacement                          (tools.py:54-68)   -> the solver's current cube pose
 
 `robot` is whatever `solver_for` accepts (pinocchio RobotWrapper, KinematicTable, GraspIK, None = built-in Nextage).
@@ -57,9 +57,26 @@ def setcubeplacement(robot, cube, oMf):
     _setcubeplacement(robot, cube, oMf)
 
 
+def _is_cube_wrapper(obj):
+    """A pinocchio wrapper of the reference's cube (cube_small.urdf: one collision geometry, LARM_HOOK / RARM_HOOK frames)."""
+    m, cm = getattr(obj, "model", None), getattr(obj, "collision_model", None)
+    try:
+        return m is not None and cm is not None and hasattr(m, "existFrame") and bool(m.existFrame("LARM_HOOK"))
+    except Exception:
+        return False
+
+
 def getcubeplacement(robot, hookname=None):
-    """tools.getcubeplacement (tools.py:54-59) as a 12-vector (rotation row-major, translation); with a hook name
-    ('LARM_HOOK' / 'RARM_HOOK') the placement of that hook frame, cube * hook offset."""
+    """tools.getcubeplacement (tools.py:54-59).  With the reference's own argument -- the CUBE wrapper -- the placement is
+    read from its pinocchio geometry object exactly as the reference does and returned as a pinocchio SE3; with a robot /
+    solver / None it is the solver's current cube pose as a 12-vector (rotation row-major, translation).  With a hook
+    name ('LARM_HOOK' / 'RARM_HOOK') the placement of that hook frame, cube * hook offset."""
+    if _is_cube_wrapper(robot):
+        cube = robot
+        oMf = cube.collision_model.geometryObjects[0].placement
+        if hookname is not None:
+            oMf = oMf * cube.data.oMf[cube.model.getFrameId(hookname)]
+        return oMf
     s = solver_for(robot)
     pose = getattr(s, "cube_pose", None)
     if pose is None:
@@ -82,29 +99,19 @@ def _cube_soa(s, dtype):
     return None if pose is None else torch.as_tensor(pose, dtype=dtype, device=s.device).reshape(1, 12).t().contiguous()
 
 
-def collision(robot, q, dtype=torch.float64):
-    """Return true if in collision, false otherwise (tools.py:25-35)."""
-    s = solver_for(robot)
+def collision(robot, q, dtype=torch.float64, cube=None):
+    """Return true if in collision, false otherwise (tools.py:25-35).  `cube`: the cube wrapper, needed only the first
+    time a pinocchio robot is seen (the solver flattens robot + cube once and is cached afterwards)."""
+    s = solver_for(robot, cube)
     return bool(s.collision_soa(_q_soa(s, q, dtype), _cube_soa(s, dtype))[0].item())
 
 
-def distanceToObstacle(robot, q, dtype=torch.float64, tol=1e-6, d_max=2.0):
-    """Shortest distance between the robot and the obstacle / table (tools.py:38-51).  The kernels answer
-    "every such pair is at least m apart" (gik_clearance_*); the distance is bracketed by evaluating a ladder of
-    margins in ONE batched call per refinement level.  Returns 0.0 when a pair intersects (hpp-fcl reports the negative
-    penetration depth there; every caller in the reference only compares the value with a positive threshold)."""
-    s = solver_for(robot)
+def distanceToObstacle(robot, q, dtype=torch.float64, d_max=2.0, cube=None):
+    """Shortest distance between the robot and the obstacle / table (tools.py:38-51): ONE launch of
+    gik_obstacle_distance_* (each pair's distance bracketed by bisection on the margin of the kernels' boolean GJK, to
+    d_max / 2^40 in float64) and one read-back.  Returns 0.0 when a pair intersects: hpp-fcl reports the negative
+    penetration depth there, and every caller in the reference only compares the value with a positive threshold
+    (path.py:61-62), so the sign below zero is not reproduced.  Capped at `d_max`."""
+    s = solver_for(robot, cube)
     s._need_scene()
-    qs, cs = _q_soa(s, q, dtype), _cube_soa(s, dtype)
-    lo, hi = 0.0, d_max
-    if not bool(s.clearance_soa(qs, cs, 0.0)[0].item()):
-        return 0.0
-    if bool(s.clearance_soa(qs, cs, hi)[0].item()):
-        return hi
-    while hi - lo > tol:                      # 16-way bracketing: ~5 rounds to 1e-6
-        ms = np.linspace(lo, hi, 18)[1:-1]
-        clear = [bool(s.clearance_soa(qs, cs, float(m))[0].item()) for m in ms]
-        k = sum(clear)                        # clearance is monotone in the margin
-        lo = ms[k - 1] if k > 0 else lo
-        hi = ms[k] if k < len(ms) else hi
-    return 0.5 * (lo + hi)
+    return float(s.obstacle_distance_soa(_q_soa(s, q, dtype), _cube_soa(s, dtype), d_max)[0].item())

@@ -55,6 +55,31 @@ def test_collision_and_clearance_match_oracle(solver, table, table_c, scene_c, c
     assert (c3[sure] == (d_def[sure] == 0)).all()
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 2e-6), (torch.float32, 2e-4)])
+def test_obstacle_distance_matches_oracle(solver, table, table_c, scene_c, c_oracle, dtype, tol):
+    # distanceToObstacle as a value (tools.py:38-51): gik_obstacle_distance_* (GJK bisection in the kernel, one launch)
+    # against the oracle's alternating-projection distances, incl. the cap and the 0 on intersection
+    n = 1203
+    Q, P = _inputs(table, n, 11)
+    d_ref = c_oracle.scene_distance(table_c, scene_c, Q, P, mode=1)            # exact for every pair (no cull)
+    qs, ps = _t(Q, dtype).t().contiguous(), _t(P, dtype).t().contiguous()
+    d = solver.obstacle_distance_soa(qs, ps, 2.0).double().cpu().numpy()
+    assert d.shape == (n,) and (d >= 0).all() and (d <= 2.0).all()
+    assert ((d == 0) == (d_ref == 0))[(d_ref == 0) | (d_ref > 10 * tol)].all()
+    assert 0.1 < (d_ref > 0).mean() < 0.95
+    assert np.abs(d - np.minimum(d_ref, 2.0)).max() < tol
+    # cap below the true distance: the value is the cap; consistent with the boolean clearance kernel
+    d_cap = solver.obstacle_distance_soa(qs, ps, 0.04).double().cpu().numpy()
+    assert np.abs(d_cap - np.minimum(d_ref, 0.04)).max() < tol
+    clear = solver.clearance_soa(qs, ps, 0.04).bool().cpu().numpy()
+    sure = np.abs(d_ref - 0.04) > 10 * tol
+    assert (clear[sure] == (d_cap[sure] >= 0.04 - tol)).all()
+    # default cube placement of the scene, and an empty batch
+    d_def = solver.obstacle_distance_soa(qs[:, :64].contiguous(), None, 2.0).double().cpu().numpy()
+    assert np.abs(d_def - np.minimum(c_oracle.scene_distance(table_c, scene_c, Q[:64], None, mode=1), 2.0)).max() < tol
+    assert solver.obstacle_distance_soa(qs[:, :0].contiguous(), None).shape == (0,)
+
+
 def test_cube_collision_matches_oracle(solver, table_c, scene_c, c_oracle):
     rng = np.random.default_rng(5)
     n = 999
@@ -163,6 +188,34 @@ def test_rrt_connect_driver_end_to_end(solver, table, table_c, scene_c, c_oracle
     mid = 0.5 * (p[:, 0] + p[:, 1])
     jumps = np.linalg.norm(np.diff(mid, axis=0), axis=1)
     assert np.quantile(jumps, 0.9) < 0.03
+
+
+def test_rrt_connect_batched_expansion(solver, table, table_c, scene_c, c_oracle, golden):
+    # expand = K tree extensions per iteration through one launch of the edge kernel (path.py:194-278 rules unchanged):
+    # expand=1 is the reference loop; both must return a valid path, the batched one in fewer iterations
+    import time
+    import gik_b200
+    q0 = np.array(golden["cases"][0]["q"]); qe = np.array(golden["cases"][1]["q"])
+    a = (np.eye(3), np.array(golden["cases"][0]["cube_p"])); b = (np.eye(3), np.array(golden["cases"][1]["cube_p"]))
+    its = {}
+    for K in (1, 8):
+        tot = 0
+        for seed in (1, 2, 3):
+            t0 = time.perf_counter()
+            path, stats = gik_b200.computepath(q0, qe, a, b, robot=solver, rng=np.random.default_rng(seed), expand=K,
+                                               generator=torch.Generator(device="cuda:0").manual_seed(seed), return_stats=True)
+            print(f"expand={K} seed={seed}: {len(path)} configurations, {stats}, {time.perf_counter() - t0:.2f} s")
+            assert len(path) >= 3 and np.array_equal(path[0], q0) and np.array_equal(path[-1], qe) and stats["expand"] == K
+            Q = np.array(path)
+            assert (Q >= table.lower - 1e-9).all() and (Q <= table.upper + 1e-9).all()
+            R, p = c_oracle.fk(table_c, Q)
+            assert np.abs(np.linalg.norm(p[:, 0] - p[:, 1], axis=1) - 0.1).max() < 3e-3
+            assert (c_oracle.scene_distance(table_c, scene_c, Q, None, mode=1, cull=0.3) > 0).all()
+            mid = 0.5 * (p[:, 0] + p[:, 1])
+            assert np.quantile(np.linalg.norm(np.diff(mid, axis=0), axis=1), 0.9) < 0.03
+            tot += stats["iterations"]
+        its[K] = tot
+    assert its[8] < its[1]
 
 
 def test_success_rate_experiment_matches_oracle(solver, table_c, scene_c, c_oracle):

@@ -65,3 +65,46 @@ def test_joint_limit_helpers_need_no_gpu(table):
     assert p[4] == table.upper[4] and p[7] == table.lower[7] and np.array_equal(p[[0, 1, 2]], [0, 0, 0])
     assert tools.jointlimitsviolated(table, q) and not tools.jointlimitsviolated(table, p)
     assert abs(tools.jointlimitscost(table, q) - max(5.0 - table.upper[4], table.lower[7] + 9.0)) < 1e-12
+
+
+def test_tools_dropin_signatures_cpu():
+    # tools.py helpers with the reference's call shapes, on a duck-typed stand-in for the pinocchio cube wrapper
+    # (tools.py:54-59: getcubeplacement takes the CUBE) -- no GPU, no pinocchio
+    import inspect
+    from gik_b200 import tools
+
+    class SE3:
+        def __init__(self, M): self.M = np.asarray(M, float)
+        def __mul__(self, o): return SE3(self.M @ o.M)
+
+    class Model:
+        def existFrame(self, name): return name in ("LARM_HOOK", "RARM_HOOK")
+        def getFrameId(self, name): return {"LARM_HOOK": 1, "RARM_HOOK": 2}[name]
+
+    class Geom: pass
+    class Bag: pass
+    place = np.eye(4); place[:3, 3] = [0.33, -0.3, 0.93]
+    hookL = np.eye(4); hookL[:3, 3] = [0.0, 0.05, 0.0]
+    cube = Bag(); cube.model = Model(); cube.data = Bag(); cube.data.oMf = [SE3(np.eye(4)), SE3(hookL), SE3(np.eye(4))]
+    g = Geom(); g.placement = SE3(place)
+    cube.collision_model = Bag(); cube.collision_model.geometryObjects = [g]
+    assert tools._is_cube_wrapper(cube) and not tools._is_cube_wrapper(None) and not tools._is_cube_wrapper(object())
+    assert np.array_equal(tools.getcubeplacement(cube).M, place)
+    assert np.allclose(tools.getcubeplacement(cube, "LARM_HOOK").M[:3, 3], [0.33, -0.25, 0.93])
+    assert np.array_equal(g.placement.M, place)                    # the stored placement is not modified
+    # same parameter names / order as the reference for the positional part of every helper
+    for name, lead in (("jointlimitscost", ["robot", "q"]), ("jointlimitsviolated", ["robot", "q"]),
+                       ("projecttojointlimits", ["robot", "q"]), ("collision", ["robot", "q"]),
+                       ("distanceToObstacle", ["robot", "q"]), ("setcubeplacement", ["robot", "cube", "oMf"])):
+        assert list(inspect.signature(getattr(tools, name)).parameters)[:len(lead)] == lead
+    assert list(inspect.signature(tools.getcubeplacement).parameters)[1] == "hookname"
+    # joint-limit helpers work without a device handle
+    t = gik_b200_table()
+    q = np.zeros(15); q[3] = 9.0
+    assert tools.jointlimitsviolated(t, q) and not tools.jointlimitsviolated(t, np.zeros(15))
+    assert tools.projecttojointlimits(t, q)[3] == t.upper[3]
+
+
+def gik_b200_table():
+    import gik_b200
+    return gik_b200.nextage_table()
