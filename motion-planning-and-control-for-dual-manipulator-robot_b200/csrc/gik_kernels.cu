@@ -34,7 +34,7 @@ template <> struct Launch<float>  { static constexpr int kMinBlocks = GIK_MINB_F
 template <> struct Launch<double> { static constexpr int kMinBlocks = GIK_MINB_F64; };
 
 enum { MODE_BATCH = 0, MODE_EDGES = 1 };
-#define GIK_FLOPS_EXEC_F32_WRIST 1111   // see gik_flops_per_iter_executed()
+#define GIK_FLOPS_EXEC_F32_WRIST 1097   // see gik_flops_per_iter_executed()
 
 template <typename T>
 struct SolveArgs {
@@ -1695,9 +1695,9 @@ size_t gik_flops_per_iter(void) { return 540 + 250 + 588 + 594 + 650 + 288 + 155
 
 // FLOPs the kernels actually EXECUTE per descent iteration of one problem (FMA = 2, MUL / ADD = 1), from the executed
 // opcode mix of the committed ncu captures (profiles/): packed instructions count both halves.
-//   fp32 packed lane kernel, spherical-wrist step (profiles/r2g_solve_f32_ncu.md)
+//   fp32 packed lane kernel, spherical-wrist step (profiles/r2k_solve_f32_ncu.md: 198.7 FFMA2 + 122.2 FMUL2 + 18.2 FADD2 + 2.2 FFMA + 14.1 FMUL + 3.6 FADD)
 //   fp32 packed lane kernel, block-Cholesky step  (profiles/r1m_solve_f32_ncu.md: 320.8 FFMA2 + 102.6 FMUL2 + 11.1 FADD2 + 52.3 FFMA + 56.9 FMUL + 24.0 FADD)
-//   fp64 pair kernel (two lanes per problem), wrist (profiles/r2c_solve_f64_ncu.md: 2 x (186.3 DFMA + 82.7 DMUL + 17.4 DADD))
+//   fp64 pair kernel (two lanes per problem), wrist (profiles/r2k_solve_f64_ncu.md: 2 x (186.3 DFMA + 82.7 DMUL + 17.4 DADD))
 //   fp64 pair kernel, block-Cholesky step          (profiles/r1i_solve_f64_ncu.md: 2 x (280.3 DFMA + 96.5 DMUL + 12.8 DADD))
 size_t gik_flops_per_iter_executed(int elem_size, int wrist) {
   if (elem_size == 4) return wrist ? GIK_FLOPS_EXEC_F32_WRIST : 1696;
