@@ -259,6 +259,9 @@ def computepath(qinit, qgoal, cubeplacementq0, cubeplacementqgoal, robot=None, c
     all `expand` goal-tree edges) are projected by ONE launch of the edge kernel each.  An edge's time is the latency of
     its own warm-started chain, so `expand` edges cost what one costs and a query needs ~1/expand of the iterations.
     `expand=1` is the reference loop step for step.  The first extension (lowest index) that connects ends the search.
+    `max_iterations` stays the reference's budget of start-tree EXTENSIONS per retry (250), i.e. ceil(250 / expand)
+    iterations: this planner connects early in a retry or not at all (the vertex nearest to qgoal in configuration space
+    keeps being the one whose straight cube path is blocked), so a retry must not become `expand` times more expensive.
     `robot`: pinocchio RobotWrapper / KinematicTable / GraspIK / None (built-in Nextage); `cube` is unused unless
     `robot` is a pinocchio wrapper.  Returns the list of configurations (empty on failure), like the reference."""
     solver = solver_for(robot, cube)
@@ -287,7 +290,7 @@ def computepath(qinit, qgoal, cubeplacementq0, cubeplacementqgoal, robot=None, c
     for retry in range(max_retries):
         G_start, G_goal = [(None, qinit)], [(None, qgoal)]
         C_start, C_goal = [a12], [b12]
-        for i in range(max_iterations):
+        for i in range(-(-max_iterations // K)):
             stats["iterations"] += 1
             q_rand, cube_rand = [], []
             for _ in range(K):
