@@ -156,18 +156,21 @@ def test_reference_sampler_box(solver, table_c, c_oracle):
 
 
 def test_warm_start_and_passive_joints(solver, table, table_c, c_oracle):
+    # random warm starts (joint-limit box scaled by 0.3) with a head joint outside its limit, 1024 problems.  Measured
+    # (tools/probes/warm_start_probe.py): 1 flag of 1024 differs, q agrees to 5e-14 at the 99 % quantile with one outlier,
+    # iteration counts equal on 99.8 %
     rng = np.random.default_rng(5)
-    n = 64
+    n = 1024
     P = make_poses(n, 31)
     Q0 = rng.uniform(table.lower, table.upper, size=(n, 15)) * 0.3
     Q0[:, 1] = 2.0                                                  # head joint OUTSIDE its limit: clamped by the first update
     qo, oko, ito, _ = c_oracle.solve(table_c, Q0, P)
     q, ok, info = solver.solve(_t(Q0), _t(P), dtype=torch.float64, return_info=True)
     q = q.cpu().numpy(); ok = ok.cpu().numpy()
-    assert (ok == oko).mean() >= 0.98
+    assert (ok != oko).sum() <= 2 and 0.3 < oko.mean() < 0.9        # >= 99.8 % of the flags
     both = ok & oko
-    # random warm starts brush singularities more often than q0 = 0: bound only the bulk here (see _assert_q_close)
-    _assert_q_close(q[both], qo[both], 1e-9, frac=0.9, tol_outlier=np.inf)
+    _assert_q_close(q[both], qo[both], 1e-9, frac=0.99, tol_outlier=1e-3, n_far=3)
+    assert (info.iters.cpu().numpy()[both] == ito[both]).mean() >= 0.995
     moved = info.iters.cpu().numpy() > 0
     assert np.allclose(q[moved, 1], table.upper[1]) and np.allclose(q[moved, 2], Q0[moved, 2])
 
@@ -246,7 +249,9 @@ def test_pair_kernel_equals_lane_kernel(solver, dtype):
     if dtype == torch.float64:
         assert torch.equal(pa[1], pb[1]) and torch.equal(pa[2], pb[2]) and torch.equal(pa[0], pb[0])
     else:
-        assert (pa[1] == pb[1]).float().mean() >= 0.9 and (pa[0] - pb[0]).abs()[:, :, (pa[1] == pb[1])].max() < 2e-3
+        # fp32 mappings differ in FMA contraction only: measured on 4096 edges (tools/probes/edge_agreement_probe.py) the
+        # step counts agree on 99.95-100 %; on these 64 edges at most one may differ
+        assert (pa[1] != pb[1]).sum().item() <= 1 and (pa[0] - pb[0]).abs()[:, :, (pa[1] == pb[1])].max() < 2e-3
 
 
 def test_wrist_form_equals_cholesky_form(solver, table):
@@ -387,9 +392,40 @@ def test_project_edges_matches_oracle(solver, table_c, c_oracle):
     path32, nv32 = gik_b200.project_edges_batch(solver, _t(q0), _t(A), _t(B), num_steps=ns, max_steps=S,
                                                 dtype=torch.float32)
     same = nv32.cpu().numpy() == nv_o
-    assert same.mean() >= 0.9
+    assert (~same).sum() <= 1                     # (rate measured at scale below: 5e-4 per edge on hard edges)
     for e in np.nonzero(same)[0]:
         assert np.abs(path32[e, :nv_o[e]].double().cpu().numpy() - path_o[e, :nv_o[e]]).max(initial=0) < 2e-3
+
+
+def test_project_edges_fp32_agrees_with_fp64_at_scale(solver):
+    # 4096 edges x 16 steps reaching far enough that a third of the edges runs out of reach: the fp32 march stops at the
+    # same step as the fp64 march (which equals the oracle step for step, test above) on >= 99.8 % of the edges
+    # (measured 99.95 %: 2 edges), a differing edge differs by ONE step -- a step near the rim of the workspace that
+    # converges late in one precision and not at all in the other -- and the configurations of the steps both marched
+    # agree to fp32 accuracy
+    from conftest import make_poses
+    E, S = 4096, 16
+    A = make_poses(E, 51, "sampler"); A[:, 11] = 0.93 + 0.2 * np.random.default_rng(1).uniform(size=E)
+    B = A.copy(); B[:, 9:] += np.random.default_rng(2).uniform(-0.25, 0.25, size=(E, 3))
+    B[::4, :9] = rot_rpy(0, 0, 0.5).reshape(9)
+    q0, ok0 = solver.solve(torch.zeros(15), _t(A), dtype=torch.float64)
+    keep = ok0.cpu().numpy()
+    A, B, q0 = A[keep], B[keep], q0[keep]
+    n = len(A)
+    assert n >= 1000
+    ns = torch.full((n,), S, dtype=torch.int32, device="cuda:0")
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        out[dt] = solver.project_edges_soa(q0.to(dt).t().contiguous(), _t(A, dt).t().contiguous(), _t(B, dt).t().contiguous(), ns, S)
+    nv64, nv32 = out[torch.float64][1].cpu().numpy(), out[torch.float32][1].cpu().numpy()
+    assert 0.3 < (nv64 == S).mean() < 0.9                                  # the batch has both complete and cut edges
+    diff = nv64 != nv32
+    print(f"fp32 vs fp64 edge march: {diff.sum()} of {n} edges stop at a different step")
+    assert diff.mean() <= 0.002 and (np.abs(nv64[diff] - nv32[diff]) <= 1).all()
+    p64, p32 = out[torch.float64][0].cpu().numpy(), out[torch.float32][0].double().cpu().numpy()
+    k = np.minimum(nv64, nv32)
+    mask = np.arange(S)[:, None] < k[None, :]                              # [S, n] steps both marched
+    assert np.abs((p64 - p32) * mask[:, None, :]).max() < 2e-3
 
 
 def test_project_path_dropin(solver, golden):
