@@ -424,7 +424,8 @@ gik_tail_kernel(const __grid_constant__ DevTable<T> tab, const DevScene<T>* __re
       if (lane < 2) {
         T cs[kActive], sn[kActive], Sy, Sz;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) sincos_<true>(qh[k], sn[k], cs[k]);
+        for (int k = 0; k < 7; ++k)      // (tip-aligned wrist step: the tip slot carries q6 - tip_psi, hand_wrist_phase1)
+          sincos_<true>((WRIST && (kNextageTZ & kTipZ) && k == 6) ? qh[k] - ac.tip_psi : qh[k], sn[k], cs[k]);
         HandState<T> hs;
         WristState<T> wst;
         if constexpr (WRIST) hand_wrist_phase1<T, 0, kNextageTZ>(ac, cs, sn, tgt, wst, Sy, Sz, r);

@@ -50,6 +50,7 @@ struct ArmConst {
   T hook_R[9];  // hook frame on the cube
   T hook_p[3];
   T rw[3];      // wrist centre (common point of the axes of chain joints 4, 5, 6) in the hand frame; spherical-wrist tables only
+  T tip_psi;    // tables with kTipZ: finv_R = Rot(z, tip_psi), so finv_R * Rot(z, -q6) = Rot(z, -(q6 - tip_psi))
 };
 
 template <typename T>
@@ -67,11 +68,17 @@ struct DevTable {
 // Zero pattern of the Nextage joint translations (NextageaOpen.urdf:580-711): chest (0,0,z) | (x,y,z) | (0,0,z) |
 // (0,y,z) | (x,0,z) | (x,0,0) | (0,0,z).  Kernels are instantiated for "no zeros known" (TZ = 0, any table of the
 // compiled topology) and for this pattern; the launcher picks the specialisation when the table has at least these zeros.
-constexpr uint32_t kNextageTZ = (3u << 0) | (3u << 6) | (1u << 9) | (1u << 13) | (6u << 15) | (3u << 18);
+constexpr uint32_t kNextageJointTZ = (3u << 0) | (3u << 6) | (1u << 9) | (1u << 13) | (6u << 15) | (3u << 18);
 // Spherical wrist: joint 5's origin lies on joint 4's axis (t[5] = (x, 0, 0), joint 4 turns about x) and on joint 6's
 // axis (t[6] = (0, 0, z), joint 6 turns about z), so the axes of chain joints 4, 5, 6 meet in one point.  Part of the
 // Nextage pattern; the undamped step then decouples into two 3x3 solves per hand (hand_wrist_phase1).
 constexpr uint32_t kWristTZ = (6u << 15) | (3u << 18);
+// Tip-aligned hand frame: the rotation of the hand frame on the tip joint is a rotation about the tip joint's own axis
+// (LARM_EFF / RARM_EFF: rpy = (0, 0, 1.5708), NextageaOpen.urdf), so in the HAND frame the tip axis is the constant
+// (0, 0, 1), the first step of the backward walk is one rotation by q6 - psi with no arithmetic, and the next one acts
+// on a matrix with four zeros: 44 of the wrist step's ~340 packed operations disappear (hand_wrist_phase1).
+constexpr uint32_t kTipZ = 1u << 24;
+constexpr uint32_t kNextageTZ = kNextageJointTZ | kTipZ;
 static_assert((kNextageTZ & kWristTZ) == kWristTZ, "the Nextage pattern includes the spherical wrist");
 
 // ------------------------------------------------------------------------------------------------------
@@ -744,20 +751,38 @@ GIK_HD void hand_wrist_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], con
   static_assert((TZ & kWristTZ) == kWristTZ, "spherical-wrist path instantiated for a table pattern without one");
   static_assert(chain_axis(4) == 0 && chain_axis(5) == 1 && chain_axis(6) == 2 && chain_axis(2) == 1 && chain_axis(3) == 1 &&
                 chain_axis(1) == 2 && chain_axis(0) == 2, "axis pattern assumed below");
-  T B[9], b[3];
+  constexpr bool TIPZ = (TZ & kTipZ) != 0;
+  T B[9], b[3], a4[3], a5[3], a6[3];
+  if constexpr (TIPZ) {
+    // finv_R * Rot(z, -q6) = Rot(z, -theta), theta = q6 - tip_psi (cs / sn of the tip slot are those of theta):
+    // B = [ct st 0; -st ct 0; 0 0 1], a6 = (0, 0, 1), a5 = (st, ct, 0).  Joint 5 (y) then acts on those zeros, and row 2
+    // of joint 4's rotation (x) starts from (s5, 0, c5).
+    const T ct = cs[OFF + 6], st = sn[OFF + 6], c5 = cs[OFF + 5], s5 = sn[OFF + 5], c4 = cs[OFF + 4], s4 = sn[OFF + 4];
+    a5[0] = st; a5[1] = ct;
+    B[0] = c5 * ct; B[3] = -(c5 * st); B[6] = s5;
+    const T b02 = -(s5 * ct), b12 = s5 * st;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
-  // joint 6 (z): its axis is constant in the hand frame; after its step the translation relative to the wrist centre is 0
-  const T a6[3] = {B[2], B[5], B[8]};
-  chain_rotate<T, 6, OFF>(cs, sn, B);
-  // joint 5 (y)
-  const T a5[3] = {B[1], B[4], B[7]};
-  chain_rotate<T, 5, OFF>(cs, sn, B);
+    for (int r = 0; r < 3; ++r) { a4[r] = B[3 * r]; b[r] = -(B[3 * r] * ac.t[5][0]); }
+    // joint 4 (x): columns 1, 2 <- (c4 b1 - s4 b2, s4 b1 + c4 b2)
+    B[1] = c4 * st - s4 * b02; B[2] = s4 * st + c4 * b02;
+    B[4] = c4 * ct - s4 * b12; B[5] = s4 * ct + c4 * b12;
+    B[7] = -(s4 * c5);         B[8] = c4 * c5;
+  } else {
 #pragma unroll
-  for (int r = 0; r < 3; ++r) b[r] = -(B[3 * r] * ac.t[5][0]);
-  // joint 4 (x): still on the wrist centre's axes -- no linear part
-  const T a4[3] = {B[0], B[3], B[6]};
-  chain_rotate<T, 4, OFF>(cs, sn, B);
+    for (int i = 0; i < 9; ++i) B[i] = ac.finv_R[i];
+    // joint 6 (z): its axis is constant in the hand frame; after its step the translation relative to the wrist centre is 0
+    a6[0] = B[2]; a6[1] = B[5]; a6[2] = B[8];
+    chain_rotate<T, 6, OFF>(cs, sn, B);
+    // joint 5 (y)
+    a5[0] = B[1]; a5[1] = B[4]; a5[2] = B[7];
+    chain_rotate<T, 5, OFF>(cs, sn, B);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) b[r] = -(B[3 * r] * ac.t[5][0]);
+    // joint 4 (x): still on the wrist centre's axes -- no linear part
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a4[r] = B[3 * r];
+    chain_rotate<T, 4, OFF>(cs, sn, B);
+  }
   chain_translate<T, 4, TZ>(ac, B, b);
   // joints 3, 2 (y, y: parallel axes, the rotation about y leaves column 1 alone), 1 (z), chest (z: the same axis as joint 1)
   const T ay[3] = {B[1], B[4], B[7]};
@@ -807,11 +832,19 @@ GIK_HD void hand_wrist_phase1(const ArmConst<T>& ac, const T (&cs)[kActive], con
     rc[r] = az[r] * w0m - ay[r] * sw;
   }
   // wrist: [a4 a5 a6] x_456 = rho
-  T n[3];
-  cross3(a5, a6, n);
-  const T rd = rcp_capped(dot3(n, a4)), g = dot3(a6, a4);
-  u[3] = dot3(n, ru) * rd; u[4] = dot3(a5, ru); u[5] = dot3(a6, ru) - g * u[3];
-  w[3] = dot3(n, rc) * rd; w[4] = dot3(a5, rc); w[5] = dot3(a6, rc) - g * w[3];
+  if constexpr (TIPZ) {
+    // a6 = (0, 0, 1), a5 = (st, ct, 0), n = a5 x a6 = (ct, -st, 0), n.a4 = c5, a6.a4 = s5
+    const T ct = a5[1], st = a5[0], s5 = a4[2];
+    const T rd = rcp_capped(cs[OFF + 5]);
+    u[3] = (ct * ru[0] - st * ru[1]) * rd; u[4] = st * ru[0] + ct * ru[1]; u[5] = ru[2] - s5 * u[3];
+    w[3] = (ct * rc[0] - st * rc[1]) * rd; w[4] = st * rc[0] + ct * rc[1]; w[5] = rc[2] - s5 * w[3];
+  } else {
+    T n[3];
+    cross3(a5, a6, n);
+    const T rd = rcp_capped(dot3(n, a4)), g = dot3(a6, a4);
+    u[3] = dot3(n, ru) * rd; u[4] = dot3(a5, ru); u[5] = dot3(a6, ru) - g * u[3];
+    w[3] = dot3(n, rc) * rd; w[4] = dot3(a5, rc); w[5] = dot3(a6, rc) - g * w[3];
+  }
   Sy = u[0] * w[0]; Sz = w[0] * w[0];
 #pragma unroll
   for (int i = 1; i < 6; ++i) { Sy += u[i] * w[i]; Sz += w[i] * w[i]; }
@@ -834,7 +867,11 @@ GIK_HD void ik_iteration(const DevTable<T>& tab, const T (&q)[kActive], const T 
                          T (&dq)[kActive], T& resid2L, T& resid2R) {
   T cs[kActive], sn[kActive];
 #pragma unroll
-  for (int i = 0; i < kActive; ++i) sincos_<FAST>(q[i], sn[i], cs[i]);
+  for (int i = 0; i < kActive; ++i) {
+    // tip-aligned wrist step: the tip joints' slots carry the angle q6 - tip_psi (hand_wrist_phase1)
+    const T ang = (WRIST && (TZ & kTipZ) && (i == 6 || i == 12)) ? q[i] - tab.arm[i / 12].tip_psi : q[i];
+    sincos_<FAST>(ang, sn[i], cs[i]);
+  }
   T SyL, SzL, SyR, SzR;
   if constexpr (WRIST) {          // lambda = 0 on a spherical-wrist table: two 3x3 solves per hand
     WristState<T> wL, wR;
@@ -884,8 +921,10 @@ GIK_HD void ik_iteration_packed(const PackedTable& pt, float q0, const F2 (&q2)[
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     float sl, cl, sr, cr;
-    sincos_<true>(q2[k].x, sl, cl);
-    sincos_<true>(q2[k].y, sr, cr);
+    // tip-aligned wrist step: the tip joint's slot carries the angle q6 - tip_psi (hand_wrist_phase1)
+    const bool tip = WRIST && (TZ & kTipZ) && k == 5;
+    sincos_<true>(tip ? q2[k].x - pt.arm.tip_psi.x : q2[k].x, sl, cl);
+    sincos_<true>(tip ? q2[k].y - pt.arm.tip_psi.y : q2[k].y, sr, cr);
     cs[1 + k] = F2(cl, cr); sn[1 + k] = F2(sl, sr);
   }
   F2 Sy, Sz, r2;

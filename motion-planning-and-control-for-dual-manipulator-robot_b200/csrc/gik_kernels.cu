@@ -858,6 +858,7 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       acr.finv_p[i] = h ? R.finv_p[i] : L.finv_p[i]; acr.tip_lin[i] = h ? R.tip_lin[i] : L.tip_lin[i];
       acr.rw[i] = h ? R.rw[i] : L.rw[i];
     }
+    acr.tip_psi = h ? R.tip_psi : L.tip_psi;
 #pragma unroll
     for (int i = 0; i < 21; ++i) acr.g6[i] = h ? R.g6[i] : L.g6[i];      // read by the fp32 instantiation only
     lim_lo[0] = tab.lo[0]; lim_hi[0] = tab.hi[0];
@@ -948,7 +949,8 @@ gik_solve_pair_kernel(const __grid_constant__ DevTable<T> tab, const __grid_cons
       HandState<T> hs;
       WristState<T> wst;
 #pragma unroll
-      for (int i = 0; i < 7; ++i) sincos_<true>(q[i], sn[i], cs[i]);
+      for (int i = 0; i < 7; ++i)        // (tip-aligned wrist step: the tip slot carries q6 - tip_psi, hand_wrist_phase1)
+        sincos_<true>((WRIST && (TZ & kTipZ) && i == 6) ? q[i] - acl.tip_psi : q[i], sn[i], cs[i]);
       // (fp64 keeps the tip products in the Gram matrix: bit-identical to the fp64 lane kernel)
       if constexpr (WRIST) hand_wrist_phase1<T, 0, TZ>(acl, cs, sn, tgt, wst, Sy, Sz, r);
       else hand_phase1<T, 0, TZ, (HOIST && sizeof(T) == 4)>(acl, cs, sn, tgt, lambda, hs, Sy, Sz, r);

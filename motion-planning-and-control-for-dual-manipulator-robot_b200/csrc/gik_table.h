@@ -110,6 +110,7 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
       const double tz = t.joint_p[chain[h][6]][2];
       for (int i = 0; i < 3; ++i) ac.rw[i] = (T)(fi_p[i] - tz * av[i]);
     }
+    ac.tip_psi = (T)atan2(R[1], R[0]);       // finv_R = R^T = Rot(z, psi) when the hand frame is tip-aligned (kTipZ below)
     for (int i = 0; i < 9; ++i) ac.hook_R[i] = (T)t.hook_R[h][i];
     for (int i = 0; i < 3; ++i) ac.hook_p[i] = (T)t.hook_p[h][i];
   }
@@ -117,6 +118,16 @@ inline int build_dev_table(const gik_table_t& t, DevTable<T>& d) {
   for (int c = 0; c < 7; ++c)
     for (int i = 0; i < 3; ++i)
       if (t.joint_p[chain[0][c]][i] == 0.0 && t.joint_p[chain[1][c]][i] == 0.0) d.tzero |= 1u << (3 * c + i);
+  {  // tip-aligned hand frames: both hand rotations are rotations about z, the tip joint's axis
+    static_assert(chain_axis(6) == 2, "kTipZ assumes a z tip axis");
+    bool tipz = true;
+    for (int h = 0; h < 2; ++h) {
+      const double* R = t.hand_R[h];
+      tipz = tipz && R[2] == 0.0 && R[5] == 0.0 && R[6] == 0.0 && R[7] == 0.0 && R[8] == 1.0 &&
+             fabs(R[0] - R[4]) < 1e-12 && fabs(R[1] + R[3]) < 1e-12 && fabs(R[0] * R[0] + R[1] * R[1] - 1.0) < 1e-12;
+    }
+    if (tipz) d.tzero |= kTipZ;
+  }
   for (int j = 0; j < t.nq; ++j) {
     d.qlo[j] = narrow_lo<T>(t.lower[j]);
     d.qhi[j] = narrow_hi<T>(t.upper[j]);
@@ -138,6 +149,7 @@ inline void build_packed_table(const DevTable<float>& d, PackedTable& p) {
     p.arm.hook_p[i] = F2(L.hook_p[i], R.hook_p[i]);
     p.arm.rw[i] = F2(L.rw[i], R.rw[i]);
   }
+  p.arm.tip_psi = F2(L.tip_psi, R.tip_psi);
   for (int k = 0; k < 6; ++k) { p.lo[k] = F2(d.lo[1 + k], d.lo[7 + k]); p.hi[k] = F2(d.hi[1 + k], d.hi[7 + k]); }
   p.lo0 = d.lo[0]; p.hi0 = d.hi[0];
 }

@@ -156,6 +156,12 @@ static int pair_impl(int ta, const double* Ra, const double* pa, const double* s
 }
 
 extern "C" {
+// structure mask the table builder derives (zero translations, spherical wrist, tip-aligned hand frames); < 0: error
+long long hostsim_table_pattern(const gik_table_t* t) {
+  DevTable<double> d;
+  const int rc = build_dev_table<double>(*t, d);
+  return rc ? (long long)rc : (long long)d.tzero;
+}
 // scalar functions of gik_core.cuh whose host and device forms share their code (polynomial atan2, log6)
 void hostsim_atan2_pos_f64(int64_t n, const double* y, const double* x, double* out) {
   for (int64_t i = 0; i < n; ++i) out[i] = atan2_pos(y[i], x[i]);

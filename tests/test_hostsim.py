@@ -100,3 +100,36 @@ def test_hostsim_damped_restarts_match_oracle(table, table_c, hostsim, c_oracle)
     d = np.abs(q[both] - qo[both]).max(axis=1)
     assert np.quantile(d, 0.9) < 1e-8 and (it[both] == ito[both]).mean() >= 0.9
     assert np.abs(r[both] - ro[both]).max() < 1e-9
+
+
+def test_hostsim_nextage_table_takes_the_specialised_wrist_step(table, table_c, hostsim):
+    # the launcher's fast path needs every bit of the Nextage pattern: zero translations, spherical wrist, and hand frames
+    # that are rotations about the tip joint's axis (kTipZ, bit 24); a hand frame tilted off that axis must lose the bit
+    # (and with it the specialised step -- the generic one then runs, same results: next test)
+    import copy, ctypes
+    f = hostsim.lib.hostsim_table_pattern
+    f.restype = ctypes.c_longlong
+    nextage = (3 << 0) | (3 << 6) | (1 << 9) | (1 << 13) | (6 << 15) | (3 << 18) | (1 << 24)
+    pat = f(ctypes.byref(table_c))
+    assert pat >= 0 and (pat & nextage) == nextage
+    t2 = copy.deepcopy(table)
+    t2.hand_R = np.array(t2.hand_R, float).copy()
+    t2.hand_R[0] = rot_rpy(0.1, 0.0, 1.5708)
+    pat2 = f(ctypes.byref(t2.to_c()))
+    assert pat2 >= 0 and not (pat2 & (1 << 24)) and (pat2 & (nextage & ~(1 << 24))) == (nextage & ~(1 << 24))
+
+
+def test_hostsim_tilted_hand_frame_uses_the_generic_step(table, hostsim, c_oracle):
+    # same robot with the left hand frame tilted off the tip axis: the builder drops kTipZ, the generic path solves it,
+    # and the result still matches the oracle
+    import copy
+    t2 = copy.deepcopy(table)
+    t2.hand_R = np.array(t2.hand_R, float).copy()
+    t2.hand_R[0] = rot_rpy(0.1, 0.0, 1.5708)
+    tc2 = t2.to_c()
+    P = make_poses(24, 13)
+    P[:, 9] = np.minimum(P[:, 9], 0.5)
+    qo, oko, ito, _ = c_oracle.solve(tc2, np.zeros((24, 15)), P)
+    q, ok, it, r = hostsim.solve(tc2, np.zeros((24, 15)), P, np.float64)
+    assert (ok == oko).all() and oko.any()
+    assert np.abs(q[oko] - qo[oko]).max() < 1e-8 and (it[oko] == ito[oko]).all()
