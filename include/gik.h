@@ -296,6 +296,23 @@ const char* gik_solve_kernel_name(gik_handle_t h, int elem_size, int64_t n, int 
 const char* gik_strerror(int code);
 const char* gik_version(void);
 
+/* Replaces the least-squares fit inside `maketraj` (control.py:63-195: degree-n Bezier curve through the planned path
+ * with position / velocity / acceleration constraints at both ends) for MANY paths at once.  The constraints pin three
+ * control points at each end; the free ones are a linear least-squares problem whose design matrix -- Bernstein basis at
+ * n_points uniform times -- is the same for every path, so the caller factors it once on the host:
+ *   basis [n_points][n_free]  Bernstein values of the free control points 3 .. n_ctrl-4   (n_free = n_ctrl - 6)
+ *   pinv  [n_free][n_points]  its pseudo-inverse
+ *   w0, w1 [n_points]         summed basis values of the three pinned control points at the start / end
+ * q0, q1 [n_paths][dim], path [n_paths][n_points][dim] (row-major, as the reference passes a path: a list of q)
+ * -> ctrl [n_paths][n_ctrl][dim] (rows 0-2 = q0, last three = q1), cost [n_paths] = squared residual of the fit
+ * (the reference accepts a fit when it is below 0.15, control.py:185).  All pointers are device pointers. */
+int gik_bezier_fit_f32(gik_handle_t h, int64_t n_paths, int32_t n_points, int32_t dim, int32_t n_ctrl, const float* pinv,
+                       const float* basis, const float* w0, const float* w1, const float* q0, const float* q1,
+                       const float* path, float* ctrl, float* cost, void* stream);
+int gik_bezier_fit_f64(gik_handle_t h, int64_t n_paths, int32_t n_points, int32_t dim, int32_t n_ctrl, const double* pinv,
+                       const double* basis, const double* w0, const double* w1, const double* q0, const double* q1,
+                       const double* path, double* ctrl, double* cost, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ class GikError(RuntimeError):
 
 def _sources():
     return [os.path.join(CSRC, f) for f in ("gik_kernels.cu", "gik_core.cuh", "gik_table.h", "gik_collide.cuh",
-                                            "gik_collide_impl.cuh")] + \
+                                            "gik_collide_impl.cuh", "gik_bezier.cuh")] + \
            [os.path.join(_HERE, "..", "include", "gik.h")]
 
 
@@ -98,6 +98,7 @@ def lib() -> ctypes.CDLL:
         getattr(L, f"gik_clearance_{sfx}").argtypes = [_P, _I64, _P, _P, ctypes.c_double, _P, _P]
         getattr(L, f"gik_cube_collision_{sfx}").argtypes = [_P, _I64, _P, _P, _P]
         getattr(L, f"gik_obstacle_distance_{sfx}").argtypes = [_P, _I64, _P, _P, ctypes.c_double, _P, _P]
+        getattr(L, f"gik_bezier_fit_{sfx}").argtypes = [_P, _I64, _I32, _I32, _I32] + [_P] * 10
     L.gik_solve_success_scratch_bytes.argtypes = [_P, _I64, ctypes.c_int]
     L.gik_solve_success_scratch_bytes.restype = ctypes.c_size_t
     L.gik_flops_per_iter.restype = ctypes.c_size_t
@@ -120,6 +121,7 @@ EXPORTS = [
     "gik_solve_rows_f32", "gik_solve_rows_f64", "gik_solve_scatter_f32", "gik_solve_scatter_f64", "gik_best_of_f32", "gik_best_of_f64", "gik_project_edges_f32", "gik_project_edges_f64",
     "gik_scene_attach", "gik_collision_f32", "gik_collision_f64", "gik_collision_sel_f32", "gik_collision_sel_f64", "gik_solve_success_f32", "gik_solve_success_f64", "gik_solve_success_scratch_bytes", "gik_clearance_f32", "gik_clearance_f64",
     "gik_cube_collision_f32", "gik_cube_collision_f64", "gik_obstacle_distance_f32", "gik_obstacle_distance_f64",
+    "gik_bezier_fit_f32", "gik_bezier_fit_f64",
     "gik_flops_per_iter", "gik_flops_per_iter_executed", "gik_bytes_per_solve", "gik_measure_fma_peak", "gik_solve_launch_dims",
     "gik_solve_kernel_name",
     "gik_strerror", "gik_version",

@@ -328,6 +328,30 @@ class GraspIK:
             self.launches += 1
         return out
 
+    def bezier_fit(self, q0: torch.Tensor, q1: torch.Tensor, path: torch.Tensor, pinv, basis, w0, w1):
+        """The least-squares fit of `maketraj` (control.py:63-195) for many paths in one launch (gik_bezier_fit_*).
+        q0, q1 [N, dim], path [N, n_points, dim] on this device; pinv [n_free, n_points], basis [n_points, n_free],
+        w0 / w1 [n_points]: the factored design matrix (trajectory.fit_operands).  -> (ctrl [N, n_free + 6, dim], cost [N])."""
+        self._chk_dev(q0, q1, path)
+        dt = path.dtype
+        if dt not in (torch.float32, torch.float64) or q0.dtype != dt or q1.dtype != dt:
+            raise TypeError("q0, q1 and path must share a float32 / float64 dtype")
+        N, n_points, dim = path.shape
+        n_free = int(pinv.shape[0])
+        if q0.shape != (N, dim) or q1.shape != (N, dim) or tuple(pinv.shape) != (n_free, n_points) or \
+                tuple(basis.shape) != (n_points, n_free) or w0.shape[0] != n_points or w1.shape[0] != n_points:
+            raise ValueError("bezier_fit: inconsistent shapes")
+        ops = [torch.as_tensor(x, dtype=dt, device=self.device).contiguous() for x in (pinv, basis, w0, w1)]
+        ctrl = torch.empty((N, n_free + 6, dim), dtype=dt, device=self.device)
+        cost = torch.empty((N,), dtype=dt, device=self.device)
+        f = getattr(self._lib, f"gik_bezier_fit_{_sfx(dt)}")
+        _cabi.check(f(self._h, N, n_points, dim, n_free + 6, *[self._ptr(x) for x in ops], self._ptr(q0.contiguous()),
+                      self._ptr(q1.contiguous()), self._ptr(path.contiguous()), self._ptr(ctrl), self._ptr(cost), self._stream()),
+                    "gik_bezier_fit")
+        if N:
+            self.launches += 1
+        return ctrl, cost
+
     def cube_collision_soa(self, cube_pose_soa: torch.Tensor) -> torch.Tensor:
         """The cube's own collision test (cube vs table / obstacle, path.py:51-52): cube_pose [12][n] -> u8 [n]."""
         self._need_scene()

@@ -8,9 +8,12 @@ curve those constraints are LINEAR in the control points and decouple completely
 and likewise P_n = P_{n-1} = P_{n-2} = q1 (the reference's own saved results, trajectory*.json, show exactly that).  What
 is left is an unconstrained linear least-squares problem in the free control points P3 .. P_{n-3} with the Bernstein
 matrix as design matrix, identical for every joint: one small `lstsq`, deterministic, instead of an iterative solver
-that "works 90 percent of the time ... pretty slow" (control.py:192).  `maketraj_batch` solves many paths at once on
-the GPU with one batched solve.  This is host / library linear algebra, not a hand-written kernel: the
-system is 15 x 15."""
+that "works 90 percent of the time ... pretty slow" (control.py:192).  `maketraj_batch` fits many paths at once
+(SURVEY 8f-4): the design matrix is the same for every path with the same number of points, so it is factored ONCE on the
+host in fp64 (`fit_operands`: Bernstein basis of the free control points and its pseudo-inverse) and CUDA tensors go
+through one launch of `gik_bezier_fit_*` (csrc/gik_bezier.cuh: a warp per path, operands in shared memory, the path read
+once); CPU tensors / numpy take the same two matrix products in numpy.  `maketraj` (one path, the reference's call) is the
+numpy form."""
 from __future__ import annotations
 
 import json
@@ -89,10 +92,32 @@ def maketraj(q0, q1, path_points, total_time, degree=DEGREE):
     return [q_of_t, q_of_t.derivative(1), q_of_t.derivative(2)], bool(cost < COST_OK)
 
 
-def maketraj_batch(q0, q1, path_points, degree=DEGREE):
-    """Many paths at once (torch tensors, any device): q0, q1 [N, dim], path_points [N, n_points, dim] ->
-    (control points [N, degree+1, dim], cost [N])."""
+def fit_operands(degree: int, n_points: int):
+    """The factored design matrix of the fit for paths of `n_points` points (fp64 numpy):
+    (pinv [n_free, n_points], basis [n_points, n_free], w0 [n_points], w1 [n_points]) -- Bernstein values of the free
+    control points 3 .. degree-3 at times linspace(0, 1, n_points) (control.py:95), their pseudo-inverse, and the summed
+    basis values of the three pinned control points at each end."""
+    if degree < 6:
+        raise ValueError("degree must be at least 6 (three control points are pinned at each end)")
+    B = bernstein_matrix(degree, np.linspace(0.0, 1.0, n_points))
+    Bf = B[:, 3:degree - 2]
+    return np.linalg.pinv(Bf), Bf.copy(), B[:, :3].sum(1), B[:, degree - 2:].sum(1)
+
+
+def maketraj_batch(q0, q1, path_points, degree=DEGREE, solver=None):
+    """Many paths at once: q0, q1 [N, dim], path_points [N, n_points, dim] -> (control points [N, degree+1, dim],
+    cost [N]).  CUDA tensors: one launch of gik_bezier_fit_* (`solver`: a GraspIK on that device; default: the built-in
+    Nextage solver -- the kernel only uses its device).  CPU tensors: the same products through torch on the host."""
     import torch
+    if path_points.is_cuda:
+        from .ops import default_solver
+        s = solver if solver is not None else default_solver(path_points.device)
+        pinv, basis, w0, w1 = fit_operands(degree, path_points.shape[-2])
+        lead = path_points.shape[:-2]
+        n_points, dim = path_points.shape[-2:]
+        ctrl, cost = s.bezier_fit(q0.reshape(-1, dim), q1.reshape(-1, dim), path_points.reshape(-1, n_points, dim),
+                                  pinv, basis, w0, w1)
+        return ctrl.reshape(*lead, degree + 1, dim), cost.reshape(lead)
     Pf, cost = _fit(q0, q1, path_points, degree, torch)
     rep0 = q0.unsqueeze(-2).expand(*q0.shape[:-1], 3, q0.shape[-1])
     rep1 = q1.unsqueeze(-2).expand(*q1.shape[:-1], 3, q1.shape[-1])

@@ -342,3 +342,35 @@ def test_success_flag_agreement_fp32(solver, table_c, scene_c, c_oracle):
         agree = (succ.bool().cpu().numpy() == oko).sum()
         assert agree >= n - 1, (mode, agree)
     assert 0.2 < oko.mean() < 0.7
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-8), (torch.float32, 2e-3)])
+def test_bezier_fit_kernel_matches_the_host_fit(solver, dtype, tol):
+    # maketraj's least-squares fit (control.py:63-195) for many paths in one launch (gik_bezier_fit_*) against the numpy
+    # closed form of trajectory.maketraj: control points, the pinned ends, the residual cost and the acceptance flag
+    from gik_b200.trajectory import maketraj, maketraj_batch, fit_operands
+    rng = np.random.default_rng(2)
+    N, n_points, dim = 301, 37, 15                                      # not a multiple of the warps per block
+    q0 = rng.normal(size=(N, dim)) * 0.2; q1 = rng.normal(size=(N, dim)) * 0.2
+    t = np.linspace(0, 1, n_points)[None, :, None]
+    paths = q0[:, None, :] * (1 - t) + q1[:, None, :] * t + 0.05 * np.sin(3 * np.pi * t) * rng.normal(size=(N, 1, dim))
+    paths[:, 0], paths[:, -1] = q0, q1
+    P, cost = maketraj_batch(_t(q0, dtype), _t(q1, dtype), _t(paths, dtype), solver=solver)
+    assert P.shape == (N, 21, dim) and cost.shape == (N,) and P.is_cuda
+    P = P.double().cpu().numpy(); cost = cost.double().cpu().numpy()
+    assert np.abs(P[:, :3] - q0[:, None]).max() < 1e-6 and np.abs(P[:, -3:] - q1[:, None]).max() < 1e-6   # P0 = P1 = P2 = q0, ...
+    for i in range(0, N, 7):
+        (q, _, _), ok = maketraj(q0[i], q1[i], paths[i], 15.0)
+        ref = np.array(q.control_points_)                                  # the Bernstein design matrix is ill-conditioned
+        assert np.abs(P[i] - ref).max() < tol * max(1.0, np.abs(ref).max())
+        pinv, basis, w0, w1 = fit_operands(20, n_points)
+        rhs = paths[i] - w0[:, None] * q0[i] - w1[:, None] * q1[i]
+        c_ref = ((basis @ ref[3:-3] - rhs) ** 2).sum()
+        assert abs(cost[i] - c_ref) < max(tol, 1e-6) * max(1.0, c_ref)
+        assert ok == bool(c_ref < 0.15)
+    # other sizes: a short path, a lower degree, an empty batch
+    P2, c2 = maketraj_batch(_t(q0[:5], dtype), _t(q1[:5], dtype), _t(paths[:5, ::4], dtype), degree=8, solver=solver)
+    (q, _, _), _ = maketraj(q0[0], q1[0], paths[0, ::4], 1.0, degree=8)
+    assert P2.shape == (5, 9, dim) and np.abs(P2[0].double().cpu().numpy() - np.array(q.control_points_)).max() < tol
+    P3, c3 = maketraj_batch(_t(q0[:0], dtype), _t(q1[:0], dtype), _t(paths[:0], dtype), solver=solver)
+    assert P3.shape == (0, 21, dim) and c3.shape == (0,)
