@@ -545,8 +545,9 @@ def run_b200(args):
         if args.gather == "fused":
             try:
                 fused = gdist.SymmetricResults(15, n_total_gather, dtype, dev)
-                collective = ("fused: the solve kernel's epilogue stores q/converged into every rank's symmetric-memory "
-                              "result arrays over NVLink (P2P st.global), then one cross-rank barrier per step")
+                collective = ("fused: pusher warps of the solve kernel copy finished 1024-problem chunks of q/converged into every rank's "
+                              "symmetric-memory result arrays over NVLink (coalesced 16-byte P2P stores) while the other blocks keep "
+                              "solving, a tail kernel copies the chunks still in flight at the end, then one cross-rank barrier per step")
             except Exception as e:      # symmetric memory unavailable on this box: keep the NCCL gather and say so
                 fused = None
                 collective += f" (fused path unavailable: {type(e).__name__})"

@@ -165,7 +165,10 @@ __device__ __forceinline__ int64_t queue_take(const SolveArgs<T>& a, int64_t n, 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kChunkShift = 10;
 constexpr int kChunk = 1 << kChunkShift;
-constexpr int kMarkShift = 13;
+#ifndef GIK_MARK_SHIFT
+#define GIK_MARK_SHIFT 13
+#endif
+constexpr int kMarkShift = GIK_MARK_SHIFT;
 constexpr int kMarkDone = 0x7fffffff;
 
 __device__ __forceinline__ int ld_relaxed(const int32_t* p) {
