@@ -34,11 +34,11 @@ class Bezier:
         self.T_min_, self.T_max_, self.mult_T_ = float(t_min), float(t_max), float(mult_t)
         self.size_ = self.degree_ = len(self.control_points_) - 1
         if self.size_ < 1 or self.T_max_ <= self.T_min_:
-            raise ValueError("Can't create Bezier curve; min bound is higher than max bound.")
+            raise ValueError(f"Bezier: needs at least two control points and t_min < t_max (got {len(self.control_points_)} points, [{self.T_min_}, {self.T_max_}])")
 
     def __call__(self, t):
         if not (self.T_min_ <= t <= self.T_max_):
-            raise ValueError("Can't evaluate Bezier curve, time t is out of range")
+            raise ValueError(f"Bezier: t = {t} is outside [{self.T_min_}, {self.T_max_}]")
         u = (t - self.T_min_) / (self.T_max_ - self.T_min_)
         pts = np.array(self.control_points_)
         for _ in range(self.degree_):                      # de Casteljau
