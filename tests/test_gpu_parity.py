@@ -318,6 +318,31 @@ def test_scatter_entry_on_one_gpu(solver):
         solver.solve_scatter_soa(q0, P, [qa[0].data_ptr()], [ca[0].data_ptr()], n_total, n_total - 2)
 
 
+def test_scatter_entry_full_grid(solver):
+    # batches that fill the machine, so the fused launch runs in its full form on ONE GPU (the 2-GPU test below is skipped
+    # on a single-GPU box): pusher block + lookout, low-water marks, the two-ended queue (warps in the high hardware slots
+    # work from the top of the slab), the tail kernel.  Three destination arrays on this device stand in for the ranks;
+    # every one must equal the plain solve bit for bit, and columns outside the slab stay untouched.
+    for n, n_total, off, dtype in ((300_000, 400_000, 65_536, torch.float32),    # packed lane kernel, vector pushes
+                                   (300_001, 400_003, 65_537, torch.float32),    # ragged: scalar pushes, partial last chunk
+                                   (120_000, 131_072, 4_096, torch.float64)):    # fp64 pair kernel
+        g = torch.Generator(device="cuda:0").manual_seed(9)
+        pos = torch.tensor([0.2, -0.4, 0.93], device="cuda:0") + torch.rand((n, 3), device="cuda:0", generator=g) * \
+            torch.tensor([0.4, 0.8, 0.47], device="cuda:0")
+        P = torch.cat([torch.eye(3, device="cuda:0").reshape(1, 9).expand(n, 9), pos], 1).t().contiguous().to(dtype)
+        q0 = torch.zeros((15, n), dtype=dtype, device="cuda:0")
+        ref = solver.solve_soa(q0, P)
+        qa = [torch.full((15, n_total), -7.0, dtype=dtype, device="cuda:0") for _ in range(3)]
+        ca = [torch.full((n_total,), 9, dtype=torch.uint8, device="cuda:0") for _ in range(3)]
+        iters, resid = solver.solve_scatter_soa(q0, P, [t.data_ptr() for t in qa], [t.data_ptr() for t in ca], n_total, off)
+        torch.cuda.synchronize()
+        for d in range(3):
+            assert torch.equal(qa[d][:, off:off + n], ref[0]) and torch.equal(ca[d][off:off + n], ref[1]), (n, off, d)
+            assert (qa[d][:, :off] == -7).all() and (qa[d][:, off + n:] == -7).all()
+            assert (ca[d][:off] == 9).all() and (ca[d][off + n:] == 9).all()
+        assert torch.equal(iters, ref[2]) and torch.equal(resid, ref[3])
+
+
 def test_fused_all_gather_two_gpus():
     # NVLink path: needs >= 2 GPUs (gpurun --gpus 2); the single-GPU round-end run skips it
     import os, subprocess, sys
