@@ -194,7 +194,7 @@ GIK_HD float atan2_pos(float y, float x) {
   p = p * t + 1.0865759085e-01f;
   p = p * t + -1.4257044926e-01f;
   p = p * t + 1.9998681172e-01f;
-  p = p * t + -3.3333323101e-01f;
+  p = p * t + -3.3333323101e-01f;     // (Estrin's scheme, half the dependent depth: config 4 25.2 -> 25.4 ms, not kept)
   float r = (a * t) * p + a;
   r = y > ax ? 1.57079632679489662f - r : r;
   return x < 0.0f ? 3.14159265358979324f - r : r;
@@ -400,10 +400,19 @@ GIK_HD void sincos_(double x, double& s, double& c) {
 template <typename T>
 struct Log6Mid { T vx, vy, vz, d0, d1, d2, c, theta, wx, wy, wz, alpha, beta; };
 
+// log6_pre_v: the same from vee(R - R^T) and tr R alone (all the common case needs of R); the diagonal m.d0..d2, read
+// only by the near-pi form, is then the caller's to fill when log6_near_pi(m) says so (hand_error_post).
+template <typename T>
+GIK_HD void log6_pre_v(T vx, T vy, T vz, T tr, Log6Mid<T>& m);
 template <typename T>
 GIK_HD void log6_pre(const T (&R)[9], Log6Mid<T>& m) {
-  const T vx = R[7] - R[5], vy = R[2] - R[6], vz = R[3] - R[1];
-  const T tr = R[0] + R[4] + R[8];
+  log6_pre_v(R[7] - R[5], R[2] - R[6], R[3] - R[1], R[0] + R[4] + R[8], m);
+  m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
+}
+template <typename T>
+GIK_HD bool log6_near_pi(const Log6Mid<T>& m) { return m.theta >= T(3.14159265358979323846 - 1e-2); }
+template <typename T>
+GIK_HD void log6_pre_v(T vx, T vy, T vz, T tr, Log6Mid<T>& m) {
   const T c = min_(max_((tr - T(1)) * T(0.5), T(-1)), T(1));
   const T s = T(0.5) * sqrt_(vx * vx + vy * vy + vz * vz);
   const T theta = atan2_pos(s, c);
@@ -416,18 +425,20 @@ GIK_HD void log6_pre(const T (&R)[9], Log6Mid<T>& m) {
   const T den = front ? s : T(1) - c;
   T alpha = T(0.5) * theta * div_(num, max_(den, Num<T>::kTinyS));
   T beta = div_(T(1) - alpha, max_(t2, Num<T>::kTinyS));
+  // (The series also SHORTENS the dependent chain of the latency-bound scalar kernels -- its inputs are ready long before
+  // the reciprocals of the general form: dropping it cost config 4 1.7 %.  The packed form below drops it.)
   if (t2 < Num<T>::kSeriesT2) {
     alpha = T(1) - t2 * (T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * T(1.0 / 30240)));
     beta = T(1.0 / 12) + t2 * (T(1.0 / 720) + t2 * (T(1.0 / 30240) + t2 * T(1.0 / 1209600)));
   }
-  m.vx = vx; m.vy = vy; m.vz = vz; m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
+  m.vx = vx; m.vy = vy; m.vz = vz;
   m.c = c; m.theta = theta; m.alpha = alpha; m.beta = beta;
 }
 
 template <typename T>
 GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
   T wx = m.wx, wy = m.wy, wz = m.wz;
-  if (m.theta >= T(3.14159265358979323846 - 1e-2)) {
+  if (log6_near_pi(m)) {
     // pinocchio's explicit branch near pi: |w_i| from the diagonal, sign from the antisymmetric part
     const T cphi = -m.c;
     const T beta = div_(m.theta * m.theta, T(1) + cphi);
@@ -447,9 +458,11 @@ GIK_HD void log6_post(const Log6Mid<T>& m, const T (&p)[3], T (&e)[6]) {
 // different data, so they run on the halves of F2 values -- packed FMAs, per-half MUFU results and selects.  The series
 // forms of alpha / beta are evaluated unconditionally and selected (7 packed FMAs instead of a divergent branch); the
 // near-pi form (rare) falls back to the scalar code on each half.
-GIK_HD void log6_pre(const F2 (&R)[9], Log6Mid<F2>& m) {
-  const F2 vx = R[7] - R[5], vy = R[2] - R[6], vz = R[3] - R[1];
-  const F2 tr = R[0] + R[4] + R[8];
+GIK_HD bool log6_near_pi(const Log6Mid<F2>& m) {
+  const float lim = 3.14159265358979323846f - 1e-2f;
+  return m.theta.x >= lim || m.theta.y >= lim;
+}
+GIK_HD void log6_pre_v(F2 vx, F2 vy, F2 vz, F2 tr, Log6Mid<F2>& m) {
   const F2 c = min_(max_((tr - F2(1.0f)) * F2(0.5f), F2(-1.0f)), F2(1.0f));
   const F2 s = F2(0.5f) * sqrt_(vx * vx + vy * vy + vz * vz);
   const F2 theta = atan2_pos(s, c);
@@ -462,18 +475,31 @@ GIK_HD void log6_pre(const F2 (&R)[9], Log6Mid<F2>& m) {
   const F2 den = sel_(front, s, F2(1.0f) - c);
   const F2 alpha_g = F2(0.5f) * theta * (num * rcp_(max_(den, tiny)));
   const F2 beta_g = (F2(1.0f) - alpha_g) * rcp_(max_(t2, tiny));
+#ifdef GIK_LOG6_SERIES_F32
   const F2 alpha_s = F2(1.0f) - t2 * (F2(1.0f / 12) + t2 * (F2(1.0f / 720) + t2 * F2(1.0f / 30240)));
   const F2 beta_s = F2(1.0f / 12) + t2 * (F2(1.0f / 720) + t2 * (F2(1.0f / 30240) + t2 * F2(1.0f / 1209600)));
   const B2 small = lt_(t2, F2(Num<float>::kSeriesT2));
   m.alpha = sel_(small, alpha_s, alpha_g);
   m.beta = sel_(small, beta_s, beta_g);
-  m.vx = vx; m.vy = vy; m.vz = vz; m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
+#else
+  // The packed kernel is bound by FMA-pipe slots, and fp32 needs no series near theta = 0: alpha = (theta / s) (1 + c) / 2
+  // is a product of factors that each keep their relative accuracy (theta is computed FROM s, so the ratio is clean),
+  // and beta = (1 - alpha) / theta^2 -- whose cancellation costs it ~1e-7 / theta^2 absolute -- enters e only as
+  // beta (w.p) w with |w| = theta: an error of ~1e-7 |p|, the same as alpha's own rounding.  Seven packed FMAs and two
+  // selects less per iteration: config 2 45.8 -> 47.1 M solves/s.
+  m.alpha = sel_(gt_(s, tiny), alpha_g, F2(1.0f));     // (exactly zero rotation error: theta = 0 would zero the product)
+  m.beta = beta_g;
+#endif
+  m.vx = vx; m.vy = vy; m.vz = vz;
   m.c = c; m.theta = theta;
+}
+GIK_HD void log6_pre(const F2 (&R)[9], Log6Mid<F2>& m) {
+  log6_pre_v(R[7] - R[5], R[2] - R[6], R[3] - R[1], R[0] + R[4] + R[8], m);
+  m.d0 = R[0]; m.d1 = R[4]; m.d2 = R[8];
 }
 
 GIK_HD void log6_post(const Log6Mid<F2>& m, const F2 (&p)[3], F2 (&e)[6]) {
-  const float lim = 3.14159265358979323846f - 1e-2f;
-  if (m.theta.x >= lim || m.theta.y >= lim) {      // pinocchio's near-pi form on either hand: scalar code per half
+  if (log6_near_pi(m)) {                           // pinocchio's near-pi form on either hand: scalar code per half
     Log6Mid<float> ml, mr;
     ml.vx = m.vx.x; ml.vy = m.vy.x; ml.vz = m.vz.x; ml.d0 = m.d0.x; ml.d1 = m.d1.x; ml.d2 = m.d2.x; ml.c = m.c.x;
     ml.theta = m.theta.x; ml.wx = m.wx.x; ml.wy = m.wy.x; ml.wz = m.wz.x; ml.alpha = m.alpha.x; ml.beta = m.beta.x;
@@ -576,6 +602,9 @@ GIK_HD void hand_error_pre(const T (&B)[9], const T (&b)[3], const T (&tgt)[12],
   }
   log6_pre(R, em.m);
 }
+// (Measured and dropped: trace and antisymmetric part of R accumulated directly -- the same 27 products, five additions
+// fewer, the diagonal only near theta = pi: config 2 fp32 45.8 -> 44.6 M solves/s, config 4 24.8 -> 25.0 ms.  Three
+// six-term accumulation chains are longer than nine three-term ones, and ptxas spilled more.)
 template <typename T>
 GIK_HD void hand_error_post(const ErrMid<T>& em, T (&e)[6]) { log6_post(em.m, em.p, e); }
 
