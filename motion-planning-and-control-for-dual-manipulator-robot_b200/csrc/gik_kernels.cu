@@ -34,7 +34,7 @@ template <> struct Launch<float>  { static constexpr int kMinBlocks = GIK_MINB_F
 template <> struct Launch<double> { static constexpr int kMinBlocks = GIK_MINB_F64; };
 
 enum { MODE_BATCH = 0, MODE_EDGES = 1 };
-#define GIK_FLOPS_EXEC_F32_WRIST 967    // see gik_flops_per_iter_executed()
+#define GIK_FLOPS_EXEC_F32_WRIST 945    // see gik_flops_per_iter_executed()
 
 template <typename T>
 struct SolveArgs {
@@ -1700,7 +1700,7 @@ size_t gik_flops_per_iter(void) { return 540 + 250 + 588 + 594 + 650 + 288 + 155
 
 // FLOPs the kernels actually EXECUTE per descent iteration of one problem (FMA = 2, MUL / ADD = 1), from the executed
 // opcode mix of the committed ncu captures (profiles/): packed instructions count both halves.
-//   fp32 packed lane kernel, spherical-wrist step (profiles/r2p_solve_f32_ncu.md: 172.4 FFMA2 + 108.5 FMUL2 + 18.2 FADD2 + 2.2 FFMA + 14.1 FMUL + 5.5 FADD)
+//   fp32 packed lane kernel, spherical-wrist step (profiles/r2s_solve_f32_ncu.md: 166.9 FFMA2 + 108.5 FMUL2 + 18.2 FADD2 + 2.2 FFMA + 14.1 FMUL + 5.5 FADD)
 //   fp32 packed lane kernel, block-Cholesky step  (profiles/r1m_solve_f32_ncu.md: 320.8 FFMA2 + 102.6 FMUL2 + 11.1 FADD2 + 52.3 FFMA + 56.9 FMUL + 24.0 FADD)
 //   fp64 pair kernel (two lanes per problem), wrist (profiles/r2p_solve_f64_ncu.md: 2 x (171.4 DFMA + 75.0 DMUL + 17.9 DADD))
 //   fp64 pair kernel, block-Cholesky step          (profiles/r1i_solve_f64_ncu.md: 2 x (280.3 DFMA + 96.5 DMUL + 12.8 DADD))
