@@ -1,10 +1,10 @@
 // gik_kernels.cu -- sm_100a kernels and the C ABI of include/gik.h.
 //
-// Mapping (DESIGN.md "Execution model"): ONE IK PROBLEM PER LANE, all state in registers, no shared memory
-// and no cross-lane traffic inside an iteration, so every issue slot of the descent loop is FP32/FP64
-// arithmetic.  The kernels are persistent: a warp owns an interleaved set of 32-problem chunks and a lane
-// whose problem finished (converged or iteration cap) stores its result and immediately pulls the next
-// problem of its warp, so the bimodal iteration count (~740 converged vs 1000 exhausted) does not idle lanes.
+// Mapping (DESIGN.md "Execution model"): ONE IK PROBLEM PER LANE (lane kernels) or per LANE PAIR (pair kernel), all
+// state in registers, no shared memory and (lane kernels) no cross-lane traffic inside an iteration, so every issue
+// slot of the descent loop is FP32/FP64 arithmetic.  The kernels are persistent: a lane whose problem finished
+// (converged or iteration cap) stores its result and takes the next problem from a global work queue, so the bimodal
+// iteration count (~740 converged vs 1000 exhausted) does not idle lanes.
 // The kinematic table travels as a __grid_constant__ kernel parameter (constant bank 0): FMAs read it as
 // c[0x0][...] operands, and a handle stays immutable and stream-safe.
 #include <cuda_runtime.h>
@@ -115,9 +115,9 @@ __device__ __forceinline__ void wait_resident(const SolveArgs<T>& a, unsigned lo
 // Plain launches: the queue word counts the items handed out, in index order.
 // Fused all-gather launches (a.top_from > 0): the word is TWO counters -- low half: items handed out from the bottom of
 // the slab, high half: items handed out from the top -- and the warps in the high hardware slots (from_top) work downwards from
-// the top.  Why: the SM's warp scheduler serves the co-resident warps of a sub-partition in strict launch order
-// (measured with GIK_FUSED_STATS: of four co-resident warps the first finishes ~790 problems per launch, the others ~430 /
-// ~190 / ~60), so a problem on a late warp lives up to 13x longer than one on an early warp and would hold the finished
+// the top.  Why: the SM's warp scheduler serves the co-resident warps of a sub-partition in strict slot order
+// (measured with GIK_FUSED_STATS, see warp_slot(): of four co-resident warps the first finishes ~760 problems per launch,
+// the others ~440 / ~180 / ~50), so a problem on a late warp lives up to 13x longer than one on an early warp and would hold the finished
 // PREFIX -- all the pushers can ship -- back by a third of the launch.  With the late warps (17 % of the throughput)
 // working at the other end, the prefix trails the queue by the early warps' problem duration only.  The two ends meet
 // wherever they meet: no tuning, no imbalance.  A problem's arithmetic does not depend on who solves it or when.
@@ -144,8 +144,8 @@ __device__ __forceinline__ int64_t queue_take(const SolveArgs<T>& a, int64_t n, 
 // Fused all-gather (gik_solve_scatter_*): the transfer half of "solve + all-gather in one kernel".
 //
 // A finished problem's result is stored into this rank's OWN result arrays (q_dst[0] / conv_dst[0]) exactly as in a
-// plain launch.  Block 0 of the grid does not solve: its warps are PUSHERS that copy finished chunks of kChunk
-// consecutive problems -- nq rows of kChunk values plus kChunk flags -- into every peer's arrays with coalesced 16-byte
+// plain launch.  The leading push_blocks blocks of the grid do not solve: one warp is a lookout, the others are PUSHERS
+// that copy finished chunks of kChunk consecutive problems -- nq rows of kChunk values plus kChunk flags -- into every peer's arrays with coalesced 16-byte
 // stores over NVLink (loads from L2), all through the launch, so the transfer overlaps the remaining solves.  A small
 // tail kernel (gik_push_rest_kernel, the whole machine) copies what is left when the last problem ends -- the chunks
 // that were still in flight -- and one cross-rank barrier follows.
@@ -153,7 +153,8 @@ __device__ __forceinline__ int64_t queue_take(const SolveArgs<T>& a, int64_t n, 
 // How a pusher knows that a chunk is finished without the solving lanes paying for it: the queue hands problems out in
 // index order, so "every problem below F is finished" holds for F = min(queue head, smallest index still being solved).
 // Each compute warp publishes a LOW-WATER MARK -- the smallest index among its lanes' current problems, in units of
-// 2^kMarkShift problems -- into marks[warp]; a pusher takes the minimum over all marks and the queue head.  A warp
+// 2^kMarkShift problems -- into marks[warp]; the lookout takes the minimum over all marks and the queue head.  (Warps
+// that work from the top of the slab -- queue_take -- never hold the prefix and publish "done" at once.)  A warp
 // recomputes its mark only when one of its lanes finishes (one REDUX), publishes it only when it changed (<= n >>
 // kMarkShift times per launch) and one finish event LATE, before that event's own result stores: the release fence in
 // front of the publication then has nothing in flight to wait for.  Stale marks are low, i.e. conservative.  [The first

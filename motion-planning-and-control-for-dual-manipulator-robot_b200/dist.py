@@ -2,9 +2,10 @@
 process per GPU, contiguous slab per rank, no collective on the data path.  When every rank needs the whole answer:
 
   * `all_gather_results`  -- ONE NCCL all-gather of (q, converged) after the kernel (the baseline), or
-  * `SymmetricResults` + `solve_sharded_fused` -- the solve kernel's own epilogue stores each result into every
-    rank's result array through NVLink peer mappings (torch symmetric memory), so no collective follows the kernel:
-    only a cross-rank barrier."""
+  * `SymmetricResults` + `solve_sharded_fused` -- solve + all-gather in ONE kernel launch: lanes store results into this
+    rank's own array, pusher warps of the same kernel copy finished 1024-problem chunks into every peer's array through
+    NVLink peer mappings (torch symmetric memory) while the other blocks keep solving, a tail kernel copies the chunks
+    still in flight at the end; no collective follows, only a cross-rank barrier."""
 from __future__ import annotations
 
 import torch
@@ -59,7 +60,7 @@ def solve_sharded(solver, q_init_soa, pose_soa, n_total: int, *, gather=True, gr
 
 class SymmetricResults:
     """Result arrays q [nq][n_total] and converged u8 [n_total] allocated as torch symmetric memory: every rank maps
-    every other rank's copy, and the fused kernel (gik_solve_scatter_*) writes into all of them.
+    every other rank's copy, and the fused launch (gik_solve_scatter_*) fills all of them.
     Reuse: call `barrier()` again before the next launch overwrites arrays a peer may still be reading."""
 
     def __init__(self, nq: int, n_total: int, dtype, device, group=None):
@@ -81,7 +82,7 @@ class SymmetricResults:
 
 
 def solve_sharded_fused(solver, q_init_soa, pose_soa, results: SymmetricResults, *, group=None, **kw):
-    """Each rank solves its slab and its kernel scatters the results into every rank's `results` arrays; returns
+    """Each rank solves its slab and the same launch copies the results into every rank's `results` arrays; returns
     (results.q, results.conv, iters_local, resid_local) after the barrier."""
     lo, hi = shard_bounds(results.n_total, results.rank, results.world)
     assert hi - lo == q_init_soa.shape[1], "local slab does not match shard_bounds"

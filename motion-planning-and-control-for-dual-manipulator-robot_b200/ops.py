@@ -209,7 +209,7 @@ class GraspIK:
         _cabi.check(f(self._h, n, self._ptr(q_init), self._ptr(pose), ctypes.byref(prm), P, qa, ca, int(n_total),
                       int(offset), self._ptr(iters), self._ptr(resid), self._stream()), "gik_solve_scatter")
         if n:
-            self.launches += 1
+            self.launches += 2 if P > 1 else 1          # solve kernel (+ its pusher blocks) and the tail kernel
         return iters, resid
 
     def best_of_soa(self, q, conv, resid, n_place: int, n_restart: int):
