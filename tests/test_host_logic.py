@@ -108,3 +108,108 @@ def test_tools_dropin_signatures_cpu():
 def gik_b200_table():
     import gik_b200
     return gik_b200.nextage_table()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The fused all-gather's bookkeeping (csrc/gik_kernels.cu: queue_take, mark_update / mark_publish, the lookout's F),
+# restated in Python and driven through random interleavings: the device code is these few integer rules plus
+# atomics, and the properties below are what makes pushing a chunk before the kernel ends safe.
+# ----------------------------------------------------------------------------------------------------------
+def _queue_take(state, n, k, from_top):
+    """One warp refill on the two-ended queue word (low half: handed out from the bottom, high half: from the top).
+    Returns the work items of the k requesting lanes (-1 = none) and whether the warp now knows the queue is exhausted."""
+    b, t = state
+    if from_top:
+        state[1] = t + k
+        cands = [n - 1 - t - r for r in range(k)]
+        items = [c if c >= b else -1 for c in cands]
+    else:
+        state[0] = b + k
+        cands = [b + r for r in range(k)]
+        items = [c if c < n - t else -1 for c in cands]
+    return items, (b + t + k >= n)
+
+
+def test_two_ended_queue_hands_every_problem_out_exactly_once():
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        n = int(rng.integers(1, 400))
+        state = [0, 0]
+        seen = []
+        exhausted = 0
+        for _ in range(10 * n + 50):                       # refills keep coming after exhaustion, like late warps
+            k = int(rng.integers(1, 33))
+            items, ex = _queue_take(state, n, k, bool(rng.integers(0, 2)))
+            seen += [i for i in items if i >= 0]
+            exhausted += ex
+            if len(seen) == n and rng.random() < 0.3:
+                break
+        assert sorted(seen) == list(range(n)), (trial, n)
+        assert exhausted >= 1                              # somebody learned that the queue ran dry
+
+
+def test_low_water_marks_never_overstate_the_finished_prefix():
+    # W warps of L lanes; bottom warps publish their low-water mark ONE finish event late, top warps publish "done" at
+    # once; the lookout's F = min(marks << shift, bottom count, n - top count) must never exceed the true finished prefix
+    # at any moment, under random finish orders and random delays between computing and publishing a mark.
+    rng = np.random.default_rng(1)
+    DONE, shift = 1 << 30, 2
+    for trial in range(60):
+        n, W, L = int(rng.integers(50, 600)), int(rng.integers(2, 7)), 4
+        top = [bool(w >= W // 2 and rng.random() < 0.8) for w in range(W)]
+        state = [0, 0]
+        finished = np.zeros(n, bool)
+        lanes = [[-1] * L for _ in range(W)]               # current problem of every lane (-1: none)
+        marks = [DONE if top[w] else 0 for w in range(W)]  # what the lookout can read
+        pending = [0] * W
+        exhausted = [False] * W
+        gone = [False] * W
+
+        def check():
+            m = min(marks)
+            F = n if m == DONE else (m << shift)
+            F = min(F, state[0], n - state[1], n)
+            prefix = int(np.argmin(finished)) if not finished.all() else n
+            assert F <= prefix, (trial, F, prefix)
+
+        def refill(w):
+            need = [j for j in range(L) if lanes[w][j] < 0]
+            if need and not exhausted[w]:
+                items, ex = _queue_take(state, n, len(need), top[w])
+                exhausted[w] = ex
+                for j, it in zip(need, items):
+                    lanes[w][j] = it
+
+        for w in range(W):
+            refill(w)
+        steps = 0
+        while not all(gone):
+            steps += 1
+            assert steps < 100000
+            w = int(rng.integers(0, W))
+            if gone[w]:
+                continue
+            active = [j for j in range(L) if lanes[w][j] >= 0]
+            if not active:
+                if exhausted[w]:
+                    marks[w] = DONE; gone[w] = True        # mark_exit (after a fence: everything it stored is visible)
+                else:
+                    refill(w)
+                check()
+                continue
+            # a finish event of this warp: publish the PREVIOUS mark, store results, retire, compute the next mark, refill
+            if not top[w] and pending[w] != marks[w]:
+                marks[w] = pending[w]
+            check()
+            for j in active:
+                if rng.random() < 0.5 or len(active) == 1:
+                    finished[lanes[w][j]] = True
+                    lanes[w][j] = -1
+            still = [lanes[w][j] >> shift for j in range(L) if lanes[w][j] >= 0]
+            if still:
+                pending[w] = min(still)
+            check()
+            refill(w)
+            check()
+        assert finished.all()
+        check()
