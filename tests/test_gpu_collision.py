@@ -374,3 +374,28 @@ def test_bezier_fit_kernel_matches_the_host_fit(solver, dtype, tol):
     assert P2.shape == (5, 9, dim) and np.abs(P2[0].double().cpu().numpy() - np.array(q.control_points_)).max() < tol
     P3, c3 = maketraj_batch(_t(q0[:0], dtype), _t(q1[:0], dtype), _t(paths[:0], dtype), solver=solver)
     assert P3.shape == (0, 21, dim) and c3.shape == (0,)
+
+
+def test_restarts_with_the_collision_term(solver):
+    # computeqgrasppose_batch(restarts=R, collision=True): every candidate gets the full predicate, the selection runs over
+    # the SUCCESSFUL candidates -- a returned success is converged and collision-free, and a placement whose restart 0
+    # (the caller's q_init) succeeds is never lost to a colliding restart with a smaller residual
+    import gik_b200
+    from conftest import make_poses
+    n, R = 96, 6
+    P = _t(make_poses(n, 77), torch.float64)
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    q1, ok1 = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), P, dtype=torch.float64, collision=True)
+    qR, okR, info = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), P, dtype=torch.float64, collision=True, restarts=R,
+                                                     generator=g, return_info=True)
+    assert qR.shape == (n, 15) and okR.shape == (n,) and info.which.shape == (n,)
+    assert (okR | ~ok1).all() and okR.sum() >= ok1.sum()                 # restart 0 is the single-start problem
+    idx = torch.nonzero(okR).flatten()
+    assert idx.numel() >= 10
+    assert (info.resid[idx] < 1e-3).all()
+    col = solver.collision_soa(qR[idx].t().contiguous(), P[idx].t().contiguous()).bool()
+    assert not col.any()
+    # without the collision term more placements "succeed" (converged but colliding ones): the term is really applied
+    _, okc = gik_b200.computeqgrasppose_batch(solver, torch.zeros(15), P, dtype=torch.float64, restarts=R,
+                                              generator=torch.Generator(device="cuda:0").manual_seed(3))
+    assert okc.sum() > okR.sum()
