@@ -28,3 +28,21 @@ for dtype in (torch.float64, torch.float32):
     e1.record(); torch.cuda.synchronize()
     print(f"{str(dtype):14s} drop-in call {wall*1e3:.3f} ms wall (success={ok}, iterations {int(out[2][0])}) | "
           f"kernel + launch {e0.elapsed_time(e1)/50:.3f} ms for one problem")
+
+# the full predicate on the device (collision term + keep-descending tail): the golden placement (740 iterations, free), and
+# the worst case -- a converged-but-colliding placement that descends to the iteration cap and is then decided by the tail
+solver.attach_scene()
+sys.path.insert(0, 'tests')
+from conftest import make_poses
+P = make_poses(96, 77)
+_, conv = solver.solve(torch.zeros(15), torch.as_tensor(P, device=dev), dtype=torch.float64)
+_, succ, _, _, _ = solver.solve_success_soa(torch.zeros((15, 96), dtype=torch.float64, device=dev),
+                                            torch.as_tensor(P, device=dev).t().contiguous())
+bad = int(torch.nonzero(conv & ~succ.bool())[0])
+for name, place in (("golden placement", cube), ("converged-but-colliding placement (worst case)", (np.eye(3), P[bad, 9:]))):
+    for _ in range(5):
+        q, ok = gik_b200.computeqgrasppose(None, q0, None, place)
+    t = time.perf_counter()
+    for _ in range(30):
+        q, ok, it, _ = gik_b200.computeqgrasppose(None, q0, None, place, return_info=True)
+    print(f"full predicate, fp64, {name}: {(time.perf_counter() - t) / 30 * 1e3:.3f} ms wall per drop-in call (success={ok}, iterations {it})")
