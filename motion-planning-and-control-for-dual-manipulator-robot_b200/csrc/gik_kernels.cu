@@ -242,10 +242,32 @@ __device__ __forceinline__ void mark_stats(const SolveArgs<T>& a, const MarkStat
   }
 }
 
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int4 ld_relaxed4(const int32_t* p) {
+  int4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_relaxed(const long long* p) {
+  long long v;
+  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(long long* p, long long v) {
+  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // pusher side -------------------------------------------------------------------------------------------------------
 // chunk ch of the slab: rows of this rank's own arrays -> the same place in every peer's arrays (one warp)
+// `stop` (in-kernel pushers only): a control word that turns non-zero when the last solve has ended; the push is then
+// abandoned between two batches of loads (returns false, the chunk stays unflagged and the tail kernel copies it whole)
+// so that the solve kernel does not outlive its last solve by the rest of a chunk -- up to 0.1 ms with 7 destinations.
 template <typename T>
-__device__ __forceinline__ void push_chunk(const SolveArgs<T>& a, int nq, int64_t n_items, int64_t ch, int lane) {
+__device__ __forceinline__ bool push_chunk(const SolveArgs<T>& a, int nq, int64_t n_items, int64_t ch, int lane,
+                                           const long long* stop = nullptr) {
   const int64_t left = n_items - (ch << kChunkShift);
   const int cs = (int)(left < kChunk ? left : kChunk);
   const int64_t c0 = a.out_off + (ch << kChunkShift);
@@ -261,6 +283,11 @@ __device__ __forceinline__ void push_chunk(const SolveArgs<T>& a, int nq, int64_
     constexpr int U = 8;
     const int wpr = cs / PER, total = nq * wpr;
     for (int k0 = lane; k0 < total; k0 += 32 * U) {
+      if (stop) {
+        long long sv = 0;
+        if (lane == 0) sv = ld_relaxed(stop);
+        if (__shfl_sync(0xffffffffu, sv, 0) != 0) return false;
+      }
       uint4 v[U];
       int64_t o[U];
 #pragma unroll
@@ -297,6 +324,7 @@ __device__ __forceinline__ void push_chunk(const SolveArgs<T>& a, int nq, int64_
       for (int d = 1; d < a.n_dst; ++d) a.conv_dst[d][c0 + k] = v;
     }
   }
+  return true;
 }
 
 // The leading push_blocks blocks of a fused launch.  Warp 0 of block 0 is the LOOKOUT: it keeps reading the queue head
@@ -309,24 +337,6 @@ __device__ __forceinline__ void push_chunk(const SolveArgs<T>& a, int nq, int64_
 // look, two thirds of the pushers' time, half of the chunks pushed in-kernel.  Pushers that finish the chunks F has
 // already passed before they look at the exit flag: the kernel outlives the last solve by 4 ms at 2 destinations and
 // 19 ms at 8, because F sweeps the last 10 % of the slab at the very end.]
-__device__ __forceinline__ unsigned long long now_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ int4 ld_relaxed4(const int32_t* p) {
-  int4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ long long ld_relaxed(const long long* p) {
-  long long v;
-  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(long long* p, long long v) {
-  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 template <typename T>
 __device__ __noinline__ void pusher_loop(const SolveArgs<T>& a, int nq, int64_t n) {
   const int lane = threadIdx.x & 31, warp = (int)blockIdx.x * (GIK_THREADS / 32) + (threadIdx.x >> 5);
@@ -411,8 +421,9 @@ __device__ __noinline__ void pusher_loop(const SolveArgs<T>& a, int nq, int64_t 
       t_b += t1 - t0;
       if (left) break;                    // the solves are over: chunk c (not flagged) and the rest go to the tail kernel
       __threadfence();                    // results are read after the F that covers them
-      push_chunk(a, nq, n, c, lane);
+      const bool whole = push_chunk(a, nq, n, c, lane, a.push_ctl + 1);
       __syncwarp();
+      if (!whole) break;                  // the solves ended while this chunk was on its way: the tail kernel redoes it
       if (lane == 0) a.pushed[c] = 1;
       t_a += now_ns() - t1;
       ++count;
