@@ -138,9 +138,11 @@ int gik_solve_rows_f64(gik_handle_t h, int64_t n, const double* q_init, const do
                        double* q_out, uint8_t* converged, int32_t* iters, double* resid,
                        const unsigned long long* ready, void* stream);
 
-/* K3 fused with its all-gather (multi-GPU): the same solve, but each rank's kernel stores its
- * results straight into the result arrays of ALL ranks through peer-mapped pointers (NVLink / NVSwitch P2P stores from
- * the kernel's epilogue), so no collective follows the kernel.  q_all[p] / conv_all[p] are HOST arrays of n_peers
+/* K3 fused with its all-gather (multi-GPU): the same solve, and the SAME launch fills the result arrays
+ * of ALL ranks through peer-mapped pointers -- lanes store into the array that lives on this device, pusher warps of
+ * the kernel copy finished 1024-problem chunks into the others with coalesced 16-byte NVLink / NVSwitch P2P stores while
+ * the remaining blocks keep solving, and a tail kernel (same stream) copies the chunks still in flight at the end -- so
+ * no collective follows.  Results are bit-identical to gik_solve_*.  q_all[p] / conv_all[p] are HOST arrays of n_peers
  * device pointers, valid on this handle's device (this rank's own buffer and the peer mappings of the others, e.g.
  * CUDA IPC or torch symmetric memory): rank p's q array [nq][n_total] and flag array [n_total].  This rank's problem i
  * lands in column offset + i of every array.  iters [n] / resid [2][n] stay local and may be NULL.  The caller
